@@ -1,0 +1,107 @@
+"""Generate golden fixtures from the REAL reference Triton kernels (executed on CPU).
+
+Run once in the build container (needs /root/reference; not available on the GPU box):
+    TRITON_INTERPRET=1 python tests/golden/make_golden.py
+The reference package cannot be imported (`sageattention/quant.py:20` needs the compiled
+`_fused`), so its Triton modules are loaded by file path; the ~30 lines of host glue around them
+(`sageattention/core.py:260-331`, `:399-448`) are restated here.  Outputs: tests/golden/*.npz
+(inputs stored as raw fp16/bf16 bit patterns so the fixtures do not depend on RNG versions).
+"""
+import os, sys, importlib.util
+os.environ["TRITON_INTERPRET"] = "1"
+import numpy as np
+import torch
+
+REF = "/root/reference/sageattention/triton"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(name):
+    spec = importlib.util.spec_from_file_location("ref_" + name, f"{REF}/{name}.py")
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m); return m
+
+
+def bits(t):
+    return t.contiguous().view(torch.int16).numpy()
+
+
+def mk(shape, dtype, seed, outlier=False):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(shape, generator=g).to(dtype)
+    k = torch.randn(shape, generator=g)
+    if outlier:
+        k = k + 4.0 * torch.randn((shape[0], shape[1], 1, shape[3]), generator=g)
+    k = k.to(dtype)
+    v = torch.randn(shape, generator=g)
+    if outlier:
+        v = v + 2.0
+    return q, k, v.to(dtype)
+
+
+def main():
+    qpb, qpt, qpbv = load("quant_per_block"), load("quant_per_thread"), load("quant_per_block_varlen")
+    att, attc = load("attn_qk_int8_per_block"), load("attn_qk_int8_per_block_causal")
+    attv, attvc = load("attn_qk_int8_block_varlen"), load("attn_qk_int8_per_block_causal_varlen")
+
+    # ---- 1. quantisation fixtures (bit-exact targets) ----------------------------------------
+    for name, shape, dtype, outlier in [
+        ("quant_d64_fp16", (1, 2, 200, 64), torch.float16, True),
+        ("quant_d128_bf16", (2, 2, 333, 128), torch.bfloat16, False),
+    ]:
+        q, k, _ = mk(shape, dtype, 1234, outlier)
+        km = k.mean(dim=2, keepdim=True)
+        D = shape[-1]
+        out = {"q": bits(q), "k": bits(k), "km": bits(km), "dtype": str(dtype)}
+        q8, qs, k8, ks = qpb.per_block_int8(q, k, km=km, sm_scale=D ** -0.5)
+        out.update(pb_q8=q8.numpy(), pb_qs=qs.numpy(), pb_k8=k8.numpy(), pb_ks=ks.numpy())
+        q8, qs, k8, ks = qpt.per_thread_int8(q, k, km)
+        out.update(pt_q8=q8.numpy(), pt_qs=qs.numpy(), pt_k8=k8.numpy(), pt_ks=ks.numpy())
+        # NHD layout variant
+        qn, kn = q.transpose(1, 2).contiguous(), k.transpose(1, 2).contiguous()
+        q8, qs, k8, ks = qpt.per_thread_int8(qn, kn, km.transpose(1, 2), tensor_layout="NHD")
+        out.update(ptn_q8=q8.numpy(), ptn_qs=qs.numpy(), ptn_k8=k8.numpy(), ptn_ks=ks.numpy())
+        np.savez_compressed(f"{HERE}/{name}.npz", **out)
+        print("wrote", name)
+
+    # ---- 2. Triton attention path (sageattn_qk_int8_pv_fp16_triton internals, core.py:260-331) ----
+    for name, shape, dtype, causal in [
+        ("attn_d64_fp16_nc", (1, 2, 320, 64), torch.float16, False),
+        ("attn_d64_fp16_c", (1, 2, 320, 64), torch.float16, True),
+        ("attn_d128_fp16_nc_ragged", (1, 2, 200, 128), torch.float16, False),
+    ]:
+        q, k, v = mk(shape, dtype, 99, True)
+        D = shape[-1]
+        km = k.mean(dim=2, keepdim=True)
+        lse_corr = torch.matmul(q, km.transpose(2, 3)).squeeze(-1).to(torch.float32)
+        sm_scale = 1.0 / (D ** 0.5)
+        q8, qs, k8, ks = qpb.per_block_int8(q, k, km=km, sm_scale=sm_scale)
+        fwd = attc.forward if causal else att.forward
+        o, lse = fwd(q8, k8, v, qs, ks, tensor_layout="HND", output_dtype=dtype, return_lse=True)
+        lse = lse / 1.44269504 + lse_corr * sm_scale
+        np.savez_compressed(f"{HERE}/{name}.npz", q=bits(q), k=bits(k), v=bits(v), o=bits(o),
+                            lse=lse.numpy(), causal=causal, dtype=str(dtype))
+        print("wrote", name)
+
+    # ---- 3. varlen (core.py:399-448) ---------------------------------------------------------
+    for name, causal in [("varlen_gqa_d128_nc", False), ("varlen_gqa_d128_c", True)]:
+        g = torch.Generator().manual_seed(7)
+        lens = [200, 130, 77]
+        T, Hq, Hk, D = sum(lens), 4, 2, 128
+        q = torch.randn((T, Hq, D), generator=g).half()
+        k = (torch.randn((T, Hk, D), generator=g) + 2.0 * torch.randn((1, Hk, D), generator=g)).half()
+        v = torch.randn((T, Hk, D), generator=g).half()
+        cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32)
+        km = k.mean(dim=0, keepdim=True)
+        ks_ = k - km
+        sm_scale = 1.0 / (D ** 0.5)
+        q8, qs, k8, ks, cuqs, cuks = qpbv.per_block_int8(q, ks_, cu, cu, max(lens), max(lens), sm_scale=sm_scale)
+        fwd = attvc.forward if causal else attv.forward
+        o = fwd(q8, k8, v, cu, cu, max(lens), qs, ks, cuqs, cuks, output_dtype=torch.float16)
+        np.savez_compressed(f"{HERE}/{name}.npz", q=bits(q), k=bits(k), v=bits(v), o=bits(o),
+                            cu=cu.numpy(), q8=q8.numpy(), qs=qs.numpy(), k8=k8.numpy(), ks=ks.numpy(),
+                            cuqs=cuqs.numpy(), cuks=cuks.numpy(), causal=causal)
+        print("wrote", name)
+
+
+if __name__ == "__main__":
+    main()
