@@ -80,4 +80,4 @@ def test_fp8_path_close_to_exact_and_to_triton_path():
             assert (o.float() - exact).abs().max().item() < 8e-2   # v has a +2 offset: fp8 V rel. error ~2%
             assert np.allclose(lse.numpy(), z["lse"], atol=5e-2)
     oc = O.sageattn_qk_int8_pv_fp8_cuda(q, k, v, is_causal=True)
-    assert (oc.float() - O.sdpa_fp32(q, k, v, is_causal=True)).abs().max().item() < 1e-1
+    assert (oc.float() - O.sdpa_fp32(q, k, v, is_causal=True)).abs().max().item() < 3e-1   # early causal rows copy single V rows: e4m3 V error ~6%
