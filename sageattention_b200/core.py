@@ -1,0 +1,209 @@
+"""Public API — drop-in for sageattention/core.py of thu-ml/SageAttention, backed by ONE sm_100a backend.
+
+Signatures and behaviour follow the reference (file:line cited per function); the bodies re-state the
+host logic (asserts, head-dim padding, K smoothing, LSE correction, output slicing) around the
+B200 kernels: fused quantisers (csrc/quant.cu) and the tcgen05 attention kernel (csrc/attn.cu).
+There is no arch dispatch, no Triton, no CPU fallback.
+"""
+from typing import Any, Optional
+import warnings
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from ._capi import SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_WARP, SAB_GRAN_PER_THREAD
+from .quant import (k_mean, per_block_int8, per_warp_int8, per_thread_int8, per_channel_fp8,
+                    per_block_int8_varlen, per_channel_fp8_varlen)
+
+_LOG2E = 1.44269504
+
+
+def _check_inputs(q, k, v):
+    assert q.is_cuda, "Input tensors must be on cuda."
+    assert q.dtype in [torch.float16, torch.bfloat16], "Input tensors must be in dtype of torch.float16 or torch.bfloat16"
+    assert q.device == k.device == v.device, "All tensors must be on the same device."
+    assert q.dtype == k.dtype == v.dtype, "All tensors must have the same dtype."
+
+
+def _pad_head_dim(q, k, v):
+    """sageattention/core.py:752-761."""
+    head_dim_og = q.size(-1)
+    if head_dim_og < 64:
+        pad = 64 - head_dim_og
+    elif 64 < head_dim_og < 128:
+        pad = 128 - head_dim_og
+    elif head_dim_og > 128:
+        raise ValueError(f"Unsupported head_dim: {head_dim_og}")
+    else:
+        pad = 0
+    if pad:
+        q, k, v = F.pad(q, (0, pad)), F.pad(k, (0, pad)), F.pad(v, (0, pad))
+    return q, k, v, head_dim_og
+
+
+def _lse_correction(q, km, tensor_layout):
+    """q @ km^T in the input dtype (sageattention/core.py:775-786)."""
+    nh_dim = 2 if tensor_layout == "NHD" else 1
+    g = q.size(nh_dim) // km.size(nh_dim)
+    kmb = torch.repeat_interleave(km, g, dim=nh_dim) if g > 1 else km
+    if tensor_layout == "NHD":
+        return torch.matmul(q.transpose(1, 2), kmb.transpose(1, 2).transpose(2, 3)).squeeze(-1).to(torch.float32)
+    return torch.matmul(q, kmb.transpose(2, 3)).squeeze(-1).to(torch.float32)
+
+
+def sageattn_qk_int8_pv_fp8_cuda(
+    q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout: str = "HND", is_causal: bool = False,
+    qk_quant_gran: str = "per_thread", sm_scale: Optional[float] = None, pv_accum_dtype: str = "fp32+fp16",
+    smooth_k: bool = True, smooth_v: bool = False, return_lse: bool = False, **kwargs: Any,
+) -> torch.Tensor:
+    """INT8 QK^T + FP8 PV attention (reference: sageattention/core.py:636-826).
+
+    pv_accum_dtype keeps the reference vocabulary.  On B200 the PV product always accumulates in fp32
+    inside the tensor core (tcgen05 f32 accumulation is full-rate, so the reference's f16 first-level
+    accumulator — a consumer-GPU speed trick — buys nothing); the option still selects the reference's V
+    quantisation range: 2.25 for "fp32+fp16", 448 otherwise (core.py:805-807).  smooth_v is honoured
+    only for "fp32" (core.py:797-803).  Unknown values raise (the reference silently returns an
+    uninitialised tensor)."""
+    dtype = q.dtype
+    _check_inputs(q, k, v)
+    assert qk_quant_gran in ["per_warp", "per_thread"], "qk_quant_gran must be either 'per_warp' or 'per_thread'."
+    if pv_accum_dtype not in ("fp32", "fp32+fp32", "fp32+fp16"):
+        raise ValueError(f"Unsupported pv_accum_dtype: {pv_accum_dtype}")
+
+    _tensor_layout = 0 if tensor_layout == "NHD" else 1
+    if tensor_layout not in ("NHD", "HND"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    q, k, v, head_dim_og = _pad_head_dim(q, k, v)
+    assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of qkv must be contiguous."
+    if is_causal:
+        seq_dim = 1 if _tensor_layout == 0 else 2
+        assert q.size(seq_dim) == k.size(seq_dim), "qo_len and kv_len must be equal for causal attention."
+    if sm_scale is None:
+        sm_scale = head_dim_og ** -0.5
+
+    lse_correction = None
+    if smooth_k:
+        km = k_mean(k, tensor_layout)
+        if return_lse:
+            lse_correction = _lse_correction(q, km, tensor_layout)
+    else:
+        km = None
+
+    if qk_quant_gran == "per_warp":
+        q_int8, q_scale, k_int8, k_scale = per_warp_int8(q, k, km, tensor_layout=tensor_layout, BLKQ=128, WARPQ=32, BLKK=64)
+        gran = SAB_GRAN_PER_WARP
+    else:
+        q_int8, q_scale, k_int8, k_scale = per_thread_int8(q, k, km, tensor_layout=tensor_layout, BLKQ=128, WARPQ=32, BLKK=64, WARPK=64)
+        gran = SAB_GRAN_PER_THREAD
+
+    o = torch.empty(q.size(), dtype=dtype, device=q.device)
+
+    if pv_accum_dtype in ("fp32+fp32", "fp32+fp16") and smooth_v:
+        warnings.warn(f"pv_accum_dtype is '{pv_accum_dtype}', smooth_v will be ignored.")
+        smooth_v = False
+    quant_v_scale_max = 2.25 if pv_accum_dtype == "fp32+fp16" else 448.0
+    v_fp8, v_scale, vm = per_channel_fp8(v, tensor_layout=tensor_layout, scale_max=quant_v_scale_max, smooth_v=smooth_v)
+
+    lse = ops.qk_int8_sv_f8_attn(q_int8, k_int8, v_fp8, o, q_scale, k_scale, v_scale, vm, _tensor_layout,
+                                 1 if is_causal else 0, gran, gran, sm_scale, 0, 1 if return_lse else 0)
+    o = o[..., :head_dim_og]
+    if return_lse:
+        return o, lse / _LOG2E + lse_correction * sm_scale if smooth_k else lse / _LOG2E
+    return o
+
+
+def sageattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout: str = "HND", is_causal: bool = False,
+             sm_scale: Optional[float] = None, return_lse: bool = False, **kwargs: Any):
+    """sageattention/core.py:79-157.  The reference dispatches on compute capability and raises on sm_100;
+    here the single B200 backend is used with the reference's sm89 defaults (per-thread INT8, FP8 PV,
+    "fp32+fp16" V range).  Unknown kwargs (attn_mask=, dropout_p=, scale=, ...) are accepted and ignored
+    exactly like the reference so SDPA monkey-patches keep working (example/cogvideox_infer.py:35)."""
+    return sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout=tensor_layout, is_causal=is_causal, sm_scale=sm_scale,
+                                        return_lse=return_lse, pv_accum_dtype="fp32+fp16")
+
+
+def sageattn_qk_int8_pv_fp8_cuda_sm90(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
+                                      qk_quant_gran: str = "per_thread", sm_scale: Optional[float] = None,
+                                      pv_accum_dtype: str = "fp32+fp32", smooth_k: bool = True, smooth_v: bool = False,
+                                      return_lse: bool = False, **kwargs: Any):
+    """API shell for sageattention/core.py:829-996 (Hopper entry point): same numerics contract, served by
+    the sm_100a kernel.  Only "fp32+fp32" exists in the reference for this entry (core.py:985-989)."""
+    assert pv_accum_dtype == "fp32+fp32", "only 'fp32+fp32' is supported for the sm90 entry point"
+    return sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout=tensor_layout, is_causal=is_causal,
+                                        qk_quant_gran=qk_quant_gran, sm_scale=sm_scale, pv_accum_dtype=pv_accum_dtype,
+                                        smooth_k=smooth_k, smooth_v=False, return_lse=return_lse)
+
+
+def sageattn_qk_int8_pv_fp16_triton(q, k, v, tensor_layout: str = "HND", quantization_backend: str = "triton",
+                                    is_causal: bool = False, sm_scale: Optional[float] = None, smooth_k: bool = True,
+                                    return_lse: bool = False, attn_mask: Optional[torch.Tensor] = None, **kwargs: Any):
+    """API shell for sageattention/core.py:160-331: per-block INT8 quantisation with the Triton path's exact
+    rounding (bit-exact q/k/scales), sm_scale*log2e folded into q, attention on the sm_100a kernel.
+    PV runs in FP8 here (the reference uses FP16 PV), so outputs agree to FP8-P accuracy.  attn_mask is
+    not supported by the B200 kernel yet."""
+    if attn_mask is not None:
+        raise NotImplementedError("attn_mask is not supported by the sm_100a kernel yet")
+    dtype = q.dtype
+    _check_inputs(q, k, v)
+    _tensor_layout = 0 if tensor_layout == "NHD" else 1
+    q, k, v, head_dim_og = _pad_head_dim(q, k, v)
+    assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of qkv must be contiguous."
+    lse_correction = None
+    if smooth_k:
+        km = k_mean(k, tensor_layout)
+        if return_lse:
+            lse_correction = _lse_correction(q, km, tensor_layout)
+    else:
+        km = None
+    if sm_scale is None:
+        sm_scale = 1.0 / (head_dim_og ** 0.5)
+    if quantization_backend not in ("triton", "cuda"):
+        raise ValueError(f"Unsupported quantization backend: {quantization_backend}")
+    q_int8, q_scale, k_int8, k_scale = per_block_int8(q, k, km=km, sm_scale=sm_scale, tensor_layout=tensor_layout,
+                                                      semantics=quantization_backend)
+    v_fp8, v_scale, _ = per_channel_fp8(v, tensor_layout=tensor_layout, scale_max=448.0, smooth_v=False)
+    o = torch.empty(q.size(), dtype=dtype, device=q.device)
+    lse = ops.qk_int8_sv_f8_attn(q_int8, k_int8, v_fp8, o, q_scale, k_scale, v_scale, None, _tensor_layout,
+                                 1 if is_causal else 0, SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_BLOCK, sm_scale, 1,
+                                 1 if return_lse else 0)
+    o = o[..., :head_dim_og]
+    if return_lse:
+        return o, lse / _LOG2E + lse_correction * sm_scale if smooth_k else lse / _LOG2E
+    return o
+
+
+def sageattn_qk_int8_pv_fp16_cuda(q, k, v, tensor_layout: str = "HND", is_causal: bool = False,
+                                  qk_quant_gran: str = "per_thread", sm_scale: Optional[float] = None,
+                                  pv_accum_dtype: str = "fp32", smooth_k: bool = True, smooth_v: bool = False,
+                                  return_lse: bool = False, **kwargs: Any):
+    """API shell for sageattention/core.py:451-633 (Ampere FP16-PV entry point), served by the INT8+FP8
+    sm_100a kernel with the 448 V range ("fp32+fp32" numerics)."""
+    return sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout=tensor_layout, is_causal=is_causal,
+                                        qk_quant_gran=qk_quant_gran, sm_scale=sm_scale, pv_accum_dtype="fp32+fp32",
+                                        smooth_k=smooth_k, smooth_v=False, return_lse=return_lse)
+
+
+def sageattn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q: torch.Tensor,
+                    cu_seqlens_k: torch.Tensor, max_seqlen_q: int, max_seqlen_k: int, is_causal: bool = False,
+                    sm_scale: Optional[float] = None, smooth_k: bool = True, **kwargs: Any) -> torch.Tensor:
+    """sageattention/core.py:334-448: packed [T,H,D] tensors, per-block INT8 per sequence (Triton rounding,
+    bit-exact), K mean over all tokens of the batch (core.py:433).  PV runs in FP8 on the sm_100a kernel
+    (the reference's Triton kernel uses FP16 PV)."""
+    dtype = q.dtype
+    _check_inputs(q, k, v)
+    q, k, v, head_dim_og = _pad_head_dim(q, k, v)
+    assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of qkv must be contiguous."
+    assert cu_seqlens_q.is_contiguous() and cu_seqlens_k.is_contiguous(), "cu_seqlens_q and cu_seqlens_k must be contiguous."
+    km = None
+    if smooth_k:
+        km = k_mean(k.unsqueeze(0), "NHD").view(1, k.size(1), k.size(2))   # mean over all tokens
+    if sm_scale is None:
+        sm_scale = 1.0 / (head_dim_og ** 0.5)
+    q_int8, q_scale, k_int8, k_scale, cu_q_scale, cu_k_scale = per_block_int8_varlen(
+        q, k, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, sm_scale=sm_scale, km=km)
+    v_fp8, v_scale, cu_pad = per_channel_fp8_varlen(v, cu_seqlens_k, max_seqlen_k, scale_max=448.0)
+    o = torch.empty(q.shape, dtype=dtype, device=q.device)
+    ops.qk_int8_sv_f8_attn_varlen(q_int8, k_int8, v_fp8, o, q_scale, k_scale, v_scale,
+                                  cu_seqlens_q.to(torch.int32), cu_seqlens_k.to(torch.int32), cu_pad, cu_q_scale,
+                                  cu_k_scale, max_seqlen_q, 1 if is_causal else 0, sm_scale, 1)
+    return o[..., :head_dim_og]

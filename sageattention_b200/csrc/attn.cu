@@ -1,0 +1,528 @@
+// Fused INT8-QK / FP8-PV attention for sm_100a (B200).
+//
+// One CTA = one 128-row Q tile of one (batch, head).  192 threads, warp-specialised:
+//   warps 0-3 : softmax / correction / epilogue — ONE THREAD PER Q ROW (TMEM lane == row), so row max and
+//               row sum need no shuffles and the O row a thread rescales is the row it owns
+//   warp 4    : TMA producer (Q once, K / V^T tiles through an NS-stage mbarrier ring, swizzled smem)
+//   warp 5    : tcgen05.mma issuer (single thread) + TMEM allocator
+// Tensor memory (256 columns per CTA, so two CTAs co-reside per SM and overlap softmax with MMA):
+//   cols [0,128)      S = Q K^T  (int32, 128x128, kind::i8)   — P (e4m3, 32 cols) is written over cols [0,32)
+//   cols [128,128+D)  O accumulator (fp32, 128xD, kind::f8f6f4, A = P from TMEM, B = V^T tile from smem)
+// Numerics follow the reference kernel csrc/qattn/qk_int_sv_f8_cuda_sm89.cuh (base-2 online softmax, the
+// -8.807 exponent offset so that P fills the e4m3 range (0,448], d accumulated from un-rounded fp32 P, mask
+// value semantics, rcp.approx / lg2.approx epilogue).  Differences, all within the stated 1e-2 tolerance:
+// the kv tile is 128 keys (reference 64) and PV accumulates in fp32 inside the tensor core across tiles.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sab {
+
+constexpr int BM = 128;  // Q rows per CTA
+constexpr int BN = 128;  // keys per kv tile
+constexpr int kNumThreads = 192;
+constexpr uint32_t kTmemCols = 256;
+constexpr float kFp8Offset = 8.807f;      // attn_utils.cuh:30
+constexpr float kMaskValue = -5000000.0f; // attn_utils.cuh:310
+constexpr int kIntSentinel = -(1 << 30);
+
+struct AttnParams {
+  const float* q_scale;
+  const float* k_scale;
+  const float* v_scale;  // nullable
+  const float* v_mean;   // nullable
+  void* out;
+  float* lse;  // nullable
+  int64_t o_stride_b, o_stride_h, o_stride_s;
+  int B, Hq, Hkv, Sq, Sk;
+  int n_q_tiles;
+  int causal;
+  float sm_scale_log2;
+  int q_mult;            // scales per 128-row Q block: 1 / 4 / 32
+  int q_gran;            // 1 / 2 / 3
+  int k_mult;            // scales per 64-key block: 1 / 4
+  int64_t qs_stride_bh;  // dense: scales per (b,h); varlen: unused
+  int64_t ks_stride_bh;
+  int qs_stride_idx;     // dense 1, varlen Hq
+  int ks_stride_idx;     // dense 1, varlen Hkv
+  const int32_t* cu_q;   // varlen (nullable)
+  const int32_t* cu_k;
+  const int32_t* cu_v;
+  const int32_t* cu_qs;
+  const int32_t* cu_ks;
+  int32_t* dbg;          // nullable debug dump (CTA 0 only)
+};
+
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+  // Bounded spin: a protocol bug traps (visible as a launch failure) instead of hanging the GPU.
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("sab: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// D: head dim (64 / 128).  kKT: per-thread K scales (4 per 64-key block) instead of 1.  OutT: __half / bf16.
+template <int D, bool kKT, typename OutT>
+__global__ void __launch_bounds__(kNumThreads, 2)
+sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int NS = (D == 128) ? 2 : 4;      // K/V ring depth
+  constexpr int SWQK = (D == 128) ? 128 : 64; // swizzle span of the Q/K tiles (= row bytes)
+  constexpr uint32_t Q_BYTES = BM * D, K_BYTES = BN * D, V_BYTES = D * BN;
+  constexpr int NG = kKT ? 8 : 2;             // dequant-scale groups per 128-key tile
+  constexpr int GPB = NG / 2;                 // groups per 64-key block
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + NS * K_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * V_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* s_full = bars + 1;
+  uint64_t* p_full = bars + 2;
+  uint64_t* o_full = bars + 3;
+  uint64_t* k_full = bars + 4;
+  uint64_t* k_empty = k_full + NS;
+  uint64_t* v_full = k_empty + NS;
+  uint64_t* v_empty = v_full + NS;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(v_empty + NS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---------------- work decode (uniform across the CTA)
+  int qt = blockIdx.x;
+  if (p.causal) qt = p.n_q_tiles - 1 - qt;  // heaviest tiles first
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int hk = h / (p.Hq / p.Hkv);
+  const bool varlen = p.cu_q != nullptr;
+  int q_len = p.Sq, kv_len = p.Sk, q_off = 0, k_off = 0, v_off = 0, tb = b;
+  int q_blk0 = 0, k_blk0 = 0;  // first 128-row / 64-key scale block of this sequence
+  if (varlen) {
+    q_off = p.cu_q[b];
+    q_len = p.cu_q[b + 1] - q_off;
+    k_off = p.cu_k[b];
+    kv_len = p.cu_k[b + 1] - k_off;
+    v_off = p.cu_v[b];
+    q_blk0 = p.cu_qs[b];
+    k_blk0 = p.cu_ks[b];
+    tb = 0;
+    if (qt * BM >= q_len) return;  // attn_qk_int8_block_varlen.py:84-85
+  }
+  int n_kv = (kv_len + BN - 1) / BN;
+  if (p.causal) n_kv = min(n_kv, qt + 1);
+  const int n_kblk = (kv_len + 63) / 64;
+
+  // ---------------- one-time setup
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(k_full + i, 1);
+      mbar_init(k_empty + i, 1);
+      mbar_init(v_full + i, 1);
+      mbar_init(v_empty + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<kTmemCols>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t tS = tmem_base;        // cols [0,128)
+  const uint32_t tP = tmem_base;        // cols [0,32) (aliases S)
+  const uint32_t tO = tmem_base + 128;  // cols [128,128+D)
+
+  if (warp == 4) {
+    // =============================== TMA producer ===============================
+    if (lane == 0 && n_kv > 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_4d(sQ, &tmQ, q_full, 0, q_off + qt * BM, h, tb);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % NS;
+        const uint32_t ph = (j / NS) & 1;
+        mbar_wait_wd(k_empty + s, ph ^ 1);
+        mbar_expect_tx(k_full + s, K_BYTES);
+        tma_load_4d(sK + s * K_BYTES, &tmK, k_full + s, 0, k_off + j * BN, hk, tb);
+        mbar_wait_wd(v_empty + s, ph ^ 1);
+        mbar_expect_tx(v_full + s, V_BYTES);
+        tma_load_4d(sV + s * V_BYTES, &tmV, v_full + s, v_off + j * BN, 0, hk, tb);
+      }
+    }
+  } else if (warp == 5) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0 && n_kv > 0) {
+      constexpr uint32_t idesc_qk = make_idesc(2, 1, 1, BM, BN);  // s32 <- s8 x s8
+      constexpr uint32_t idesc_pv = make_idesc(1, 0, 0, BM, D);   // f32 <- e4m3 x e4m3
+      const uint64_t dQ = make_smem_desc<SWQK>(smem_u32(sQ));
+      mbar_wait_wd(q_full, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % NS;
+        const uint32_t ph = (j / NS) & 1;
+        mbar_wait_wd(k_full + s, ph);
+        tc_fence_after();
+        const uint64_t dK = make_smem_desc<SWQK>(smem_u32(sK + s * K_BYTES));
+#pragma unroll
+        for (int k = 0; k < D / 32; ++k) umma_i8_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_qk, k > 0);
+        tc_commit(k_empty + s);  // K stage reusable once the MMAs retire
+        tc_commit(s_full);       // S(j) ready (also implies PV(j-1) retired: in-order pipe)
+        mbar_wait_wd(p_full, j & 1);
+        tc_fence_after();
+        mbar_wait_wd(v_full + s, ph);
+        tc_fence_after();
+        const uint64_t dV = make_smem_desc<128>(smem_u32(sV + s * V_BYTES));
+#pragma unroll
+        for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tO, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
+        tc_commit(v_empty + s);
+      }
+      tc_commit(o_full);
+    }
+  } else {
+    // =============================== softmax / correction / epilogue ===============================
+    const int row = warp * 32 + lane;  // TMEM lane == Q row inside the tile
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int q_row = qt * BM + row;  // row index inside the sequence
+    const bool dump = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+
+    // per-row Q dequant scale (qk_int_sv_f8_cuda_sm89.cuh:98-114)
+    int q_idx = (q_blk0 + qt) * p.q_mult;
+    if (p.q_gran == SAB_GRAN_PER_WARP) q_idx += row >> 5;
+    if (p.q_gran == SAB_GRAN_PER_THREAD) q_idx += (row >> 5) * 8 + (row & 7);
+    const float* qs_base = p.q_scale + (varlen ? int64_t(h) : (int64_t(b) * p.Hq + h) * p.qs_stride_bh);
+    const float* ks_base = p.k_scale + (varlen ? int64_t(hk) : (int64_t(b) * p.Hkv + hk) * p.ks_stride_bh);
+    const float qss = qs_base[int64_t(q_idx) * p.qs_stride_idx] * p.sm_scale_log2;
+
+    float m = kMaskValue;  // running max (log2 units, includes the -8.807 offset)
+    float d = 0.f;         // running sum of fp32 P
+
+    for (int j = 0; j < n_kv; ++j) {
+      // dequant coefficient per scale group of this tile (…sm89.cuh:116-132, 255-257)
+      float coef[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int blk = 2 * j + g / GPB;
+        float ks = 0.f;
+        if (blk < n_kblk) ks = ks_base[int64_t((k_blk0 + blk) * GPB + g % GPB) * p.ks_stride_idx];
+        coef[g] = ks * qss;
+      }
+      // number of visible keys of this tile for this row (OOB + causal, attn_utils.cuh:296-351)
+      int limit = kv_len - j * BN;
+      if (p.causal) limit = min(limit, q_row - j * BN + 1);
+      const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && j >= qt);
+
+      mbar_wait_wd(s_full, j & 1);
+      tc_fence_after();
+
+      // ---- pass 1: row max.  Scales are positive, so max_c(S_c*coef_g(c)) = max_g(coef_g * max_{c in g} S_c):
+      //      integer max per scale group, 8 (or 2) int->float conversions per row instead of 128.
+      int gmax[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) gmax[g] = kIntSentinel;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_off + ch * 32, r);
+        tc_wait_ld();
+        if (dump && j == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p.dbg[row * 128 + ch * 32 + i] = int(r[i]);
+        }
+        if (masked_tile) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i >= limit) r[i] = uint32_t(kIntSentinel);
+        }
+        if constexpr (kKT) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            int v = gmax[(ch / 2) * 4 + t];
+#pragma unroll
+            for (int i8 = 0; i8 < 32; i8 += 8) v = __vimax3_s32(v, int(r[i8 + 2 * t]), int(r[i8 + 2 * t + 1]));
+            gmax[(ch / 2) * 4 + t] = v;
+          }
+        } else {
+          int v = gmax[ch / 2];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) v = __vimax3_s32(v, int(r[i]), int(r[i + 1]));
+          gmax[ch / 2] = v;
+        }
+      }
+      float mx = kMaskValue;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float c = (gmax[g] == kIntSentinel) ? kMaskValue : float(gmax[g]) * coef[g];
+        mx = fmaxf(mx, c);
+      }
+      const float m_new = fmaxf(m, mx - kFp8Offset);  // update_mdo, attn_utils.cuh:377-396
+      const float alpha = ex2_approx(m - m_new);
+      d *= alpha;
+
+      // ---- correction: rescale this row of O (in TMEM).  PV(j-1) has retired (s_full(j) ordering).
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(tO + lane_off + ch * 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st32(tO + lane_off + ch * 32, r);
+        }
+      }
+
+      // ---- pass 2: P = exp2(S*coef - m_new) -> e4m3 into TMEM (over S), d += sum(P)
+      const float nm = -m_new;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_off + ch * 32, r);
+        tc_wait_ld();
+        float pf[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          // exact int32 -> fp32 for |S| < 2^22 via the 1.5*2^23 magic constant (no I2F on the slow pipe)
+          const float sf = __uint_as_float(r[i] + 0x4B400000u) - 12582912.0f;
+          const int g = (ch / 2) * GPB + (kKT ? ((i & 7) >> 1) : 0);
+          float e = ex2_approx(fmaf(sf, coef[g], nm));
+          if (masked_tile && (ch * 32 + i >= limit)) e = 0.f;
+          pf[i] = e;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          acc0 += pf[i];
+          acc1 += pf[i + 1];
+          acc2 += pf[i + 2];
+          acc3 += pf[i + 3];
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) pk[w] = pack_e4m3x4(pf[4 * w], pf[4 * w + 1], pf[4 * w + 2], pf[4 * w + 3]);
+        tmem_st8(tP + lane_off + ch * 8, pk);
+        if (dump && j == 0) {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) p.dbg[128 * 128 + row * 32 + ch * 8 + w] = int(pk[w]);
+        }
+      }
+      d += (acc0 + acc1) + (acc2 + acc3);
+      m = m_new;
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / d * v_scale (+ v_mean) -> fp16/bf16, 16-byte stores (…sm89.cuh:572-703)
+    OutT* orow = reinterpret_cast<OutT*>(p.out) + (varlen ? 0 : int64_t(b) * p.o_stride_b) + int64_t(h) * p.o_stride_h +
+                 int64_t(q_off + q_row) * p.o_stride_s;
+    const bool row_ok = q_row < q_len;
+    const float* vs = p.v_scale ? p.v_scale + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D : nullptr;
+    const float* vm = p.v_mean ? p.v_mean + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D : nullptr;
+    if (n_kv > 0) {
+      mbar_wait_wd(o_full, 0);
+      tc_fence_after();
+      const float inv = rcp_approx(d);
+#pragma unroll
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tO + lane_off + ch * 32, r);
+        tc_wait_ld();
+        if (dump) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p.dbg[128 * 128 + 128 * 32 + row * D + ch * 32 + i] = int(r[i]);
+        }
+        uint32_t o16[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a = __uint_as_float(r[i]) * inv, c = __uint_as_float(r[i + 1]) * inv;
+          if (vs) {
+            a *= vs[ch * 32 + i];
+            c *= vs[ch * 32 + i + 1];
+          }
+          if (vm) {
+            a += vm[ch * 32 + i];
+            c += vm[ch * 32 + i + 1];
+          }
+          o16[i / 2] = pack2<OutT>(a, c);
+        }
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) dst[v4] = make_uint4(o16[4 * v4], o16[4 * v4 + 1], o16[4 * v4 + 2], o16[4 * v4 + 3]);
+        }
+      }
+      if (dump) {
+        p.dbg[128 * 128 + 128 * 32 + 128 * D + row] = __float_as_int(d);
+        p.dbg[128 * 128 + 128 * 32 + 128 * D + 128 + row] = __float_as_int(m);
+      }
+    } else if (row_ok) {
+      uint4* dst = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+      for (int v4 = 0; v4 < D / 8; ++v4) dst[v4] = make_uint4(0, 0, 0, 0);
+    }
+    if (p.lse != nullptr && row_ok) {
+      // log2 units like the reference kernel (…sm89.cuh:691-703); the offset cancels: log2(sum 2^x)
+      const int64_t li = varlen ? (int64_t(h) * p.Sq + q_off + q_row) : ((int64_t(b) * p.Hq + h) * p.Sq + q_row);
+      p.lse[li] = n_kv > 0 ? lg2_approx(d) + m : -INFINITY;
+    }
+  }
+
+  // ---------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 4-D byte tensor map: dims (innermost first) d0..d3, strides in bytes for d1..d3, box (b0,b1,1,1).
+static int make_map_u8(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                       uint64_t s1, uint64_t s2, uint64_t s3, uint32_t b0, uint32_t b1, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  SAB_REQUIRE(fn != nullptr, SAB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[4] = {d0, d1, d2 ? d2 : 1, d3 ? d3 : 1};
+  cuuint64_t strides[3] = {s1, s2 ? s2 : s1 * dims[1], s3 ? s3 : (s2 ? s2 : s1 * dims[1]) * dims[2]};
+  cuuint32_t box[4] = {b0, b1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i)
+    SAB_REQUIRE(strides[i] % 16 == 0, SAB_ERR_INVALID, "tensor stride %d (%llu bytes) must be a multiple of 16",
+                i + 1, (unsigned long long)strides[i]);
+  SAB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, SAB_ERR_INVALID, "tensor base must be 16-byte aligned");
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SAB_REQUIRE(r == CUDA_SUCCESS, SAB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+  return SAB_OK;
+}
+
+template <int D, bool kKT, typename OutT>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                       dim3 grid, cudaStream_t stream) {
+  constexpr int NS = (D == 128) ? 2 : 4;
+  // 1 KB alignment slack + tiles + barriers; at least 80 KB so that exactly two CTAs (2 x 256 TMEM columns) fit an SM
+  size_t smem = 1024 + size_t(BM) * D + size_t(NS) * 2 * BN * D + 256;
+  if (smem < 80 * 1024) smem = 80 * 1024;
+  auto kern = sage_attn_fwd_kernel<D, kKT, OutT>;
+  static bool configured = false;
+  if (!configured) {
+    SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, smem, stream>>>(tq, tk, tv, p);
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
+}
+
+}  // namespace sab
+
+extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8, const uint8_t* v_fp8, void* out,
+                                      float* lse, const float* q_scale, const float* k_scale, const float* v_scale,
+                                      const float* v_mean, int out_dtype, int B, int Hq, int Hkv, int Sq, int Skv,
+                                      int D, int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
+                                      int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_s, int64_t v_s_pad,
+                                      int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s, int is_causal,
+                                      int q_gran, int k_gran, float sm_scale, int fold_sm_scale,
+                                      const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
+                                      const int32_t* cu_pad_v, const int32_t* cu_q_scale, const int32_t* cu_k_scale,
+                                      int max_seqlen_q, int32_t* debug_dump, void* stream) {
+  using namespace sab;
+  SAB_REQUIRE(q_int8 && k_int8 && v_fp8 && out && q_scale && k_scale, SAB_ERR_INVALID, "null tensor pointer");
+  SAB_REQUIRE(D == 64 || D == 128, SAB_ERR_UNSUPPORTED, "Unsupported head dim: %d (64 or 128 after padding)", D);
+  SAB_REQUIRE(out_dtype == SAB_DTYPE_FP16 || out_dtype == SAB_DTYPE_BF16, SAB_ERR_UNSUPPORTED, "output dtype must be fp16 or bf16");
+  SAB_REQUIRE(B > 0 && Hq > 0 && Hkv > 0 && Sq > 0 && Skv >= 0, SAB_ERR_INVALID, "bad sizes B=%d Hq=%d Hkv=%d Sq=%d Skv=%d", B, Hq, Hkv, Sq, Skv);
+  SAB_REQUIRE(Hq % Hkv == 0, SAB_ERR_INVALID, "num_qo_heads (%d) must be divisible by num_kv_heads (%d)", Hq, Hkv);
+  SAB_REQUIRE(q_gran >= 1 && q_gran <= 3 && k_gran >= 1 && k_gran <= 3, SAB_ERR_INVALID, "unknown quant granularity q=%d k=%d", q_gran, k_gran);
+  SAB_REQUIRE(v_s_pad % 128 == 0 && v_s_pad >= Skv, SAB_ERR_INVALID, "v_fp8 token dimension (%lld) must be a multiple of 128 and >= kv_len", (long long)v_s_pad);
+  SAB_REQUIRE(aligned16(out) && o_stride_s % 8 == 0 && o_stride_h % 8 == 0 && o_stride_b % 8 == 0, SAB_ERR_INVALID, "output must be 16-byte aligned with strides multiple of 8 elements");
+  const bool varlen = cu_seqlens_q != nullptr;
+  if (varlen)
+    SAB_REQUIRE(cu_seqlens_k && cu_pad_v && cu_q_scale && cu_k_scale && max_seqlen_q > 0, SAB_ERR_INVALID, "varlen needs cu_seqlens_k, cu_pad_v, cu_q_scale, cu_k_scale and max_seqlen_q");
+  int st = sab_check_device();
+  if (st != SAB_OK) return st;
+
+  CUtensorMap tq, tk, tv;
+  const int swqk = D == 128 ? 128 : 64;
+  if (!varlen) {
+    if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, B, q_stride_s, q_stride_h, q_stride_b, D, BM, swqk))) return st;
+    if ((st = make_map_u8(&tk, k_int8, D, Skv > 0 ? Skv : 1, Hkv, B, k_stride_s, k_stride_h, k_stride_b, D, BN, swqk))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, B, v_s_pad, uint64_t(v_s_pad) * D, uint64_t(v_s_pad) * D * Hkv, BN, D, 128))) return st;
+  } else {
+    // packed [T,H,D]: Sq / Skv are the TOTAL token counts
+    if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, 1, q_stride_s, q_stride_h, 0, D, BM, swqk))) return st;
+    if ((st = make_map_u8(&tk, k_int8, D, Skv, Hkv, 1, k_stride_s, k_stride_h, 0, D, BN, swqk))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, 1, v_s_pad, uint64_t(v_s_pad) * D, 0, BN, D, 128))) return st;
+  }
+
+  AttnParams p{};
+  p.q_scale = q_scale; p.k_scale = k_scale; p.v_scale = v_scale; p.v_mean = v_mean;
+  p.out = out; p.lse = lse;
+  p.o_stride_b = o_stride_b; p.o_stride_h = o_stride_h; p.o_stride_s = o_stride_s;
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.Sq = Sq; p.Sk = Skv;
+  const int max_q = varlen ? max_seqlen_q : Sq;
+  p.n_q_tiles = (max_q + BM - 1) / BM;
+  p.causal = is_causal ? 1 : 0;
+  p.sm_scale_log2 = fold_sm_scale ? 1.0f : sm_scale * 1.44269504088896340736f;
+  p.q_gran = q_gran;
+  p.q_mult = q_gran == SAB_GRAN_PER_BLOCK ? 1 : (q_gran == SAB_GRAN_PER_WARP ? 4 : 32);
+  p.k_mult = k_gran == SAB_GRAN_PER_THREAD ? 4 : 1;
+  p.qs_stride_bh = int64_t((Sq + BM - 1) / BM) * p.q_mult;
+  p.ks_stride_bh = int64_t((Skv + 63) / 64) * p.k_mult;
+  p.qs_stride_idx = varlen ? Hq : 1;
+  p.ks_stride_idx = varlen ? Hkv : 1;
+  p.cu_q = cu_seqlens_q; p.cu_k = cu_seqlens_k; p.cu_v = cu_pad_v; p.cu_qs = cu_q_scale; p.cu_ks = cu_k_scale;
+  p.dbg = debug_dump;
+
+  dim3 grid(p.n_q_tiles, Hq, B);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool kt = k_gran == SAB_GRAN_PER_THREAD;
+  const bool bf = out_dtype == SAB_DTYPE_BF16;
+#define SAB_LAUNCH(DD, KT, T) return launch_attn<DD, KT, T>(tq, tk, tv, p, grid, s)
+  if (D == 128) {
+    if (kt) { if (bf) SAB_LAUNCH(128, true, __nv_bfloat16); else SAB_LAUNCH(128, true, __half); }
+    else    { if (bf) SAB_LAUNCH(128, false, __nv_bfloat16); else SAB_LAUNCH(128, false, __half); }
+  } else {
+    if (kt) { if (bf) SAB_LAUNCH(64, true, __nv_bfloat16); else SAB_LAUNCH(64, true, __half); }
+    else    { if (bf) SAB_LAUNCH(64, false, __nv_bfloat16); else SAB_LAUNCH(64, false, __half); }
+  }
+#undef SAB_LAUNCH
+}

@@ -1,0 +1,463 @@
+// Quantisation front-end for sm_100a: K-smoothing mean, INT8 quantisation of Q/K (per-block / per-warp /
+// per-thread granularity, CUDA or Triton rounding semantics), per-channel FP8 quantisation of V into the
+// token-contiguous V^T layout the tcgen05 PV MMA consumes.  All kernels are HBM-streaming: 128-bit loads,
+// one read of the input (+ one statistics pre-pass where the algorithm needs a full-sequence reduction),
+// 64/128-bit stores.  Semantics follow csrc/fused/fused.cu and sageattention/triton/quant_per_*.py of the
+// reference (see include/sageattn_b200.h for the per-entry citations).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace sab {
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]) {
+  uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = to_f<T>(e[i]);
+}
+
+__device__ __forceinline__ int8_t cvt_rni_sat_s8(float x) {  // csrc/numeric_conversion.cuh:144-148
+  int r;
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return static_cast<int8_t>(r);
+}
+__device__ __forceinline__ uint32_t pack_e4m3x4_q(float a, float b, float c, float d) {
+  uint32_t r;
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 lo, %2, %1;\n\t"
+      "cvt.rn.satfinite.e4m3x2.f32 hi, %4, %3;\n\t"
+      "mov.b32 %0, {lo, hi};\n\t}"
+      : "=r"(r)
+      : "f"(a), "f"(b), "f"(c), "f"(d));
+  return r;
+}
+
+// =====================================================================================================
+// Channel statistics over the token dimension: per (b,h,d) sum / max / min.  Two deterministic stages
+// (no atomics): stage 1 reduces 1024-token chunks, stage 2 folds the chunk partials in order.
+// =====================================================================================================
+constexpr int kStatChunk = 1024;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) channel_stats_stage1(const T* __restrict__ x, float* __restrict__ part, int S,
+                                                             int64_t sb, int64_t sh, int64_t ss, int nchunk) {
+  constexpr int TPR = D / 8;        // threads per token row
+  constexpr int RPP = 256 / TPR;    // rows per pass
+  const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
+  const T* base = x + b * sb + h * sh + tc * 8;
+  float sum[8], mx[8], mn[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sum[i] = 0.f; mx[i] = -INFINITY; mn[i] = INFINITY; }
+  const int r0 = chunk * kStatChunk;
+  const int r1 = min(S, r0 + kStatChunk);
+  for (int r = r0 + tr; r < r1; r += RPP) {
+    float f[8];
+    load8<T>(base + int64_t(r) * ss, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sum[i] += f[i]; mx[i] = fmaxf(mx[i], f[i]); mn[i] = fminf(mn[i], f[i]); }
+  }
+  __shared__ float s_sum[RPP][D + 1], s_mx[RPP][D + 1], s_mn[RPP][D + 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s_sum[tr][tc * 8 + i] = sum[i]; s_mx[tr][tc * 8 + i] = mx[i]; s_mn[tr][tc * 8 + i] = mn[i]; }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float a = 0.f, m1 = -INFINITY, m2 = INFINITY;
+    for (int r = 0; r < RPP; ++r) { a += s_sum[r][threadIdx.x]; m1 = fmaxf(m1, s_mx[r][threadIdx.x]); m2 = fminf(m2, s_mn[r][threadIdx.x]); }
+    float* o = part + ((int64_t(b) * gridDim.y + h) * nchunk + chunk) * 3 * D;
+    o[threadIdx.x] = a; o[D + threadIdx.x] = m1; o[2 * D + threadIdx.x] = m2;
+  }
+}
+
+// mode 0: K mean -> T [B,H,D].  mode 1: V scale (+ mean) -> fp32.
+template <typename T>
+__global__ void channel_stats_stage2(const float* __restrict__ part, int nchunk, int D, int S, int mode, T* mean_out,
+                                     float* scale_out, float* vmean_out, float scale_max, float* recp_out) {
+  const int bh = blockIdx.x, d = threadIdx.x;
+  if (d >= D) return;
+  const float* p = part + int64_t(bh) * nchunk * 3 * D;
+  float a = 0.f, m1 = -INFINITY, m2 = INFINITY;
+  for (int c = 0; c < nchunk; ++c) { a += p[c * 3 * D + d]; m1 = fmaxf(m1, p[c * 3 * D + D + d]); m2 = fminf(m2, p[c * 3 * D + 2 * D + d]); }
+  if (mode == 0) {
+    mean_out[int64_t(bh) * D + d] = from_f<T>(__fdiv_rn(a, float(S)));  // torch.mean: fp32 sum / N, cast
+  } else {
+    float amax;
+    if (vmean_out) {  // smooth_v: fused.cu:375-386 (mean over the 16-padded length)
+      const float mean = __fdiv_rn(a, float((S + 15) / 16 * 16));
+      vmean_out[int64_t(bh) * D + d] = mean;
+      amax = fmaxf(fabsf(m1 - mean), fabsf(m2 - mean));
+    } else {
+      amax = fmaxf(fabsf(m1), fabsf(m2));
+    }
+    scale_out[int64_t(bh) * D + d] = __fdividef(amax, scale_max);             // fused.cu:389
+    recp_out[int64_t(bh) * D + d] = amax > 0.f ? __fdividef(scale_max, amax) : 0.f;  // fused.cu:392 (guarded)
+  }
+}
+
+// =====================================================================================================
+// INT8 quantisation of a 128-row tile of one (b,h): per-row amax -> per-group amax -> scale -> int8.
+// =====================================================================================================
+enum GroupMode { kGroupBlock = 0, kGroupThreadQ = 1, kGroupThreadK = 2 };
+
+struct QuantParams {
+  const void* x; const void* mean; int8_t* out; float* scale;
+  int H, S, scale_cols;
+  int64_t xsb, xsh, xss, osb, osh, oss;
+  int blk;            // rows per scale group (kGroupBlock)
+  int semantics;      // SAB_SEM_*
+  int has_sm_scale; float sm_scale;
+  int eps_after;      // Triton per-thread: scale = amax/127 + 1e-7
+  // varlen (nullable): packed [T,H,D]
+  const int32_t* cu; const int32_t* cu_scale;
+};
+
+template <typename T, int D, int MODE>
+__global__ void __launch_bounds__(256) quant_int8_kernel(const QuantParams p) {
+  constexpr int TPR = D / 8;
+  constexpr int RPP = 256 / TPR;     // 16 (D=128) / 32 (D=64)
+  constexpr int NP = 128 / RPP;      // passes: 8 / 4
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
+  int S = p.S;
+  int64_t x_off, o_off;
+  int scale_row0 = 0;
+  const bool varlen = p.cu != nullptr;
+  if (varlen) {
+    const int t0 = p.cu[b];
+    S = p.cu[b + 1] - t0;
+    if (tile * 128 >= S) return;
+    x_off = int64_t(t0) * p.xss + int64_t(h) * p.xsh;
+    o_off = int64_t(t0) * p.oss + int64_t(h) * p.osh;
+    scale_row0 = p.cu_scale[b];
+  } else {
+    x_off = int64_t(b) * p.xsb + int64_t(h) * p.xsh;
+    o_off = int64_t(b) * p.osb + int64_t(h) * p.osh;
+  }
+  const T* xb = reinterpret_cast<const T*>(p.x) + x_off + tc * 8;
+  int8_t* ob = p.out + o_off + tc * 8;
+
+  float mean[8];
+  if (p.mean != nullptr) {
+    load8<T>(reinterpret_cast<const T*>(p.mean) + (int64_t(varlen ? 0 : b) * p.H + h) * D + tc * 8, mean);
+  }
+
+  __shared__ float s_row_amax[128];
+  __shared__ float s_scale[32];
+
+  float v[NP][8];
+#pragma unroll
+  for (int ps = 0; ps < NP; ++ps) {
+    const int r = ps * RPP + tr;
+    const int row = tile * 128 + r;
+    float amax = 0.f;
+    if (row < S) {
+      load8<T>(xb + int64_t(row) * p.xss, v[ps]);
+      if (p.mean != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float t = v[ps][i] - mean[i];
+          if (p.semantics == SAB_SEM_TRITON) t = to_f<T>(from_f<T>(t));  // `k - km` rounds to the input dtype
+          v[ps][i] = t;
+        }
+      }
+      if (p.has_sm_scale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[ps][i] *= p.sm_scale;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[ps][i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[ps][i] = 0.f;
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (tc == 0) s_row_amax[r] = amax;
+  }
+  __syncthreads();
+
+  // ---- group amax -> scale
+  int ngroups;
+  if (MODE == kGroupBlock) ngroups = 128 / p.blk;
+  else if (MODE == kGroupThreadQ) ngroups = 32;
+  else ngroups = 8;
+  if (threadIdx.x < ngroups) {
+    const int g = threadIdx.x;
+    float amax = 0.f;
+    if (MODE == kGroupBlock) {
+      for (int r = g * p.blk; r < (g + 1) * p.blk; ++r) amax = fmaxf(amax, s_row_amax[r]);
+    } else if (MODE == kGroupThreadQ) {  // rows {g%8 + 8i} of 32-row block g/8
+      for (int i = 0; i < 4; ++i) amax = fmaxf(amax, s_row_amax[(g / 8) * 32 + i * 8 + (g % 8)]);
+    } else {                             // keys {8j + 2t, 8j + 2t + 1} of 64-key block g/4
+      for (int j8 = 0; j8 < 8; ++j8) {
+        amax = fmaxf(amax, s_row_amax[(g / 4) * 64 + j8 * 8 + (g % 4) * 2]);
+        amax = fmaxf(amax, s_row_amax[(g / 4) * 64 + j8 * 8 + (g % 4) * 2 + 1]);
+      }
+    }
+    float scale, mult;
+    if (p.semantics == SAB_SEM_CUDA) {   // fused.cu:147-184 (compiled with --use_fast_math there)
+      amax = fmaxf(amax, 0.0000001f);
+      scale = __fdividef(amax, 127.0f);
+      mult = __fdividef(127.0f, amax);
+    } else {
+      scale = __fdiv_rn(amax, 127.0f);
+      if (p.eps_after) scale += 0.0000001f;
+      mult = scale;
+    }
+    s_scale[g] = mult;
+    const int gcol = tile * ngroups + g;
+    if (varlen) {
+      const int nblk = (S + p.blk - 1) / p.blk;
+      if (gcol < nblk) p.scale[int64_t(scale_row0 + gcol) * p.H + h] = scale;
+    } else if (gcol < p.scale_cols) {
+      p.scale[(int64_t(b) * p.H + h) * p.scale_cols + gcol] = scale;
+    }
+  }
+  __syncthreads();
+
+  // ---- quantise + store
+#pragma unroll
+  for (int ps = 0; ps < NP; ++ps) {
+    const int r = ps * RPP + tr;
+    const int row = tile * 128 + r;
+    if (row >= S) continue;
+    int g;
+    if (MODE == kGroupBlock) g = r / p.blk;
+    else if (MODE == kGroupThreadQ) g = (r / 32) * 8 + (r % 8);
+    else g = (r / 64) * 4 + (r % 8) / 2;
+    const float mult = s_scale[g];
+    int8_t q[8];
+    if (p.semantics == SAB_SEM_CUDA) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = cvt_rni_sat_s8(v[ps][i] * mult);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = __fdiv_rn(v[ps][i], mult);
+        y = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);   // quant_per_block.py:43-45
+        q[i] = static_cast<int8_t>(static_cast<int>(y));  // truncation toward zero
+      }
+    }
+    *reinterpret_cast<uint2*>(ob + int64_t(row) * p.oss) = *reinterpret_cast<uint2*>(q);
+  }
+}
+
+// =====================================================================================================
+// V: per-channel scale, e4m3, transpose to [.., D, S_pad] (token-contiguous).  One CTA = 128 tokens.
+// =====================================================================================================
+struct VQuantParams {
+  const void* v; uint8_t* out; const float* recp; const float* vmean;
+  int H, S; int64_t sb, sh, ss; int64_t s_pad; float scale_max;
+  const int32_t* cu; const int32_t* cu_pad;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) v_quant_transpose_kernel(const VQuantParams p) {
+  constexpr int TPR = D / 8;
+  constexpr int RPP = 256 / TPR;
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  int S = p.S, tok0 = 0;
+  int64_t col0 = int64_t(tile) * 128;
+  const bool varlen = p.cu != nullptr;
+  if (varlen) {
+    tok0 = p.cu[b];
+    S = p.cu[b + 1] - tok0;
+    if (tile * 128 >= S) return;
+    col0 += p.cu_pad[b];
+  }
+  __shared__ __align__(16) T s_in[128][D + 8];  // +8 elements: conflict-free column reads
+  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
+  const T* vb = reinterpret_cast<const T*>(p.v) + (varlen ? int64_t(tok0) * p.ss : int64_t(b) * p.sb) + int64_t(h) * p.sh + tc * 8;
+#pragma unroll
+  for (int r = tr; r < 128; r += RPP) {
+    const int row = tile * 128 + r;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (row < S) raw = *reinterpret_cast<const uint4*>(vb + int64_t(row) * p.ss);
+    *reinterpret_cast<uint4*>(&s_in[r][tc * 8]) = raw;
+  }
+  __syncthreads();
+  // thread -> (channel d, 32-token segment): 32 bytes = one full sector per thread
+  const int bh = (varlen ? 0 : b) * p.H + h;
+  for (int task = threadIdx.x; task < D * 4; task += 256) {
+    const int d = task % D, seg = task / D;
+    const float recp = p.recp[int64_t(bh) * D + d];      // scale_max / amax
+    const float mean = p.vmean ? p.vmean[int64_t(bh) * D + d] : 0.f;
+    uint32_t w[8];
+#pragma unroll
+    for (int q4 = 0; q4 < 8; ++q4) {
+      float f[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = seg * 32 + q4 * 4 + i;
+        float x = to_f<T>(s_in[t][d]);
+        x = (tile * 128 + t < S) ? (x - mean) * recp : 0.f;
+        f[i] = x;
+      }
+      w[q4] = pack_e4m3x4_q(f[0], f[1], f[2], f[3]);
+    }
+    uint8_t* dst = p.out + (int64_t(bh) * D + d) * p.s_pad + col0 + seg * 32;
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+static int check_common(const void* x, int dtype, int D, int64_t s0, int64_t s1, int64_t s2) {
+  SAB_REQUIRE(x != nullptr, SAB_ERR_INVALID, "null input pointer");
+  SAB_REQUIRE(dtype == SAB_DTYPE_FP16 || dtype == SAB_DTYPE_BF16, SAB_ERR_UNSUPPORTED, "Only half and bfloat16 are supported");
+  SAB_REQUIRE(D == 64 || D == 128, SAB_ERR_UNSUPPORTED, "Unsupported head dim: %d", D);
+  SAB_REQUIRE(aligned16(x) && s0 % 8 == 0 && s1 % 8 == 0 && s2 % 8 == 0, SAB_ERR_INVALID,
+              "input must be 16-byte aligned with strides multiple of 8 elements");
+  return SAB_OK;
+}
+
+template <typename T, int D>
+static int launch_stats(const void* x, float* part, int B, int H, int S, int64_t sb, int64_t sh, int64_t ss, cudaStream_t st) {
+  const int nchunk = (S + kStatChunk - 1) / kStatChunk;
+  channel_stats_stage1<T, D><<<dim3(nchunk, H, B), 256, 0, st>>>(reinterpret_cast<const T*>(x), part, S, sb, sh, ss, nchunk);
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
+}
+
+static int run_stats(const void* x, int dtype, float* part, int B, int H, int S, int D, int64_t sb, int64_t sh, int64_t ss, cudaStream_t st) {
+  if (dtype == SAB_DTYPE_FP16) return D == 128 ? launch_stats<__half, 128>(x, part, B, H, S, sb, sh, ss, st) : launch_stats<__half, 64>(x, part, B, H, S, sb, sh, ss, st);
+  return D == 128 ? launch_stats<__nv_bfloat16, 128>(x, part, B, H, S, sb, sh, ss, st) : launch_stats<__nv_bfloat16, 64>(x, part, B, H, S, sb, sh, ss, st);
+}
+
+template <typename T, int D>
+static int launch_quant_t(const QuantParams& p, int mode, dim3 grid, cudaStream_t st) {
+  if (mode == kGroupBlock) quant_int8_kernel<T, D, kGroupBlock><<<grid, 256, 0, st>>>(p);
+  else if (mode == kGroupThreadQ) quant_int8_kernel<T, D, kGroupThreadQ><<<grid, 256, 0, st>>>(p);
+  else quant_int8_kernel<T, D, kGroupThreadK><<<grid, 256, 0, st>>>(p);
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
+}
+static int launch_quant(const QuantParams& p, int dtype, int D, int mode, dim3 grid, cudaStream_t st) {
+  if (dtype == SAB_DTYPE_FP16) return D == 128 ? launch_quant_t<__half, 128>(p, mode, grid, st) : launch_quant_t<__half, 64>(p, mode, grid, st);
+  return D == 128 ? launch_quant_t<__nv_bfloat16, 128>(p, mode, grid, st) : launch_quant_t<__nv_bfloat16, 64>(p, mode, grid, st);
+}
+
+}  // namespace sab
+
+using namespace sab;
+
+extern "C" int64_t sab_k_mean_workspace_bytes(int B, int H, int S, int D) {
+  const int64_t nchunk = (S + kStatChunk - 1) / kStatChunk;
+  return int64_t(B) * H * nchunk * 3 * D * sizeof(float);
+}
+extern "C" int64_t sab_per_channel_fp8_workspace_bytes(int B, int H, int S, int D) {
+  return sab_k_mean_workspace_bytes(B, H, S, D) + int64_t(B) * H * D * sizeof(float);
+}
+
+extern "C" int sab_k_mean(const void* k, int dtype, void* mean, int B, int H, int S, int D, int64_t stride_b,
+                          int64_t stride_h, int64_t stride_s, void* workspace, void* stream) {
+  int st = check_common(k, dtype, D, stride_b, stride_h, stride_s);
+  if (st) return st;
+  SAB_REQUIRE(mean && workspace && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_k_mean");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if ((st = run_stats(k, dtype, reinterpret_cast<float*>(workspace), B, H, S, D, stride_b, stride_h, stride_s, s))) return st;
+  const int nchunk = (S + kStatChunk - 1) / kStatChunk;
+  if (dtype == SAB_DTYPE_FP16)
+    channel_stats_stage2<__half><<<B * H, 128, 0, s>>>(reinterpret_cast<float*>(workspace), nchunk, D, S, 0, reinterpret_cast<__half*>(mean), nullptr, nullptr, 0.f, nullptr);
+  else
+    channel_stats_stage2<__nv_bfloat16><<<B * H, 128, 0, s>>>(reinterpret_cast<float*>(workspace), nchunk, D, S, 0, reinterpret_cast<__nv_bfloat16*>(mean), nullptr, nullptr, 0.f, nullptr);
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
+}
+
+extern "C" int sab_quant_per_block_int8(const void* x, int dtype, const void* mean, int8_t* out, float* scale, int B,
+                                        int H, int S, int D, int64_t x_stride_b, int64_t x_stride_h, int64_t x_stride_s,
+                                        int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s, int scale_cols,
+                                        int blk, int semantics, int has_sm_scale, float sm_scale, void* stream) {
+  int st = check_common(x, dtype, D, x_stride_b, x_stride_h, x_stride_s);
+  if (st) return st;
+  SAB_REQUIRE(out && scale && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_quant_per_block_int8");
+  SAB_REQUIRE(blk == 16 || blk == 32 || blk == 64 || blk == 128, SAB_ERR_UNSUPPORTED, "Unsupported block size: %d", blk);
+  SAB_REQUIRE(semantics == SAB_SEM_CUDA || semantics == SAB_SEM_TRITON, SAB_ERR_INVALID, "unknown semantics %d", semantics);
+  SAB_REQUIRE(scale_cols >= (S + blk - 1) / blk, SAB_ERR_INVALID, "scale_cols %d < ceil(S/blk)", scale_cols);
+  SAB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 7) == 0 && o_stride_s % 8 == 0 && o_stride_h % 8 == 0 && o_stride_b % 8 == 0, SAB_ERR_INVALID, "int8 output must be 8-byte aligned");
+  QuantParams p{};
+  p.x = x; p.mean = mean; p.out = out; p.scale = scale; p.H = H; p.S = S; p.scale_cols = scale_cols;
+  p.xsb = x_stride_b; p.xsh = x_stride_h; p.xss = x_stride_s; p.osb = o_stride_b; p.osh = o_stride_h; p.oss = o_stride_s;
+  p.blk = blk; p.semantics = semantics; p.has_sm_scale = has_sm_scale; p.sm_scale = sm_scale; p.eps_after = 0;
+  // scale columns beyond the last 128-row tile (possible only when the caller over-allocates) are left untouched;
+  // the reference per_warp layout ceil(S/128)*4 is fully covered by the tiles.
+  return launch_quant(p, dtype, D, kGroupBlock, dim3((S + 127) / 128, H, B), reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sab_quant_per_thread_int8(const void* x, int dtype, const void* mean, int8_t* out, float* scale, int B,
+                                         int H, int S, int D, int64_t x_stride_b, int64_t x_stride_h, int64_t x_stride_s,
+                                         int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s, int scale_cols,
+                                         int is_key, void* stream) {
+  int st = check_common(x, dtype, D, x_stride_b, x_stride_h, x_stride_s);
+  if (st) return st;
+  SAB_REQUIRE(out && scale && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_quant_per_thread_int8");
+  const int need = is_key ? (S + 63) / 64 * 4 : (S + 127) / 128 * 32;
+  SAB_REQUIRE(scale_cols >= need, SAB_ERR_INVALID, "scale_cols %d < %d", scale_cols, need);
+  QuantParams p{};
+  p.x = x; p.mean = mean; p.out = out; p.scale = scale; p.H = H; p.S = S; p.scale_cols = scale_cols;
+  p.xsb = x_stride_b; p.xsh = x_stride_h; p.xss = x_stride_s; p.osb = o_stride_b; p.osh = o_stride_h; p.oss = o_stride_s;
+  p.blk = is_key ? 64 : 32; p.semantics = SAB_SEM_TRITON; p.has_sm_scale = 0; p.sm_scale = 1.f; p.eps_after = 1;
+  return launch_quant(p, dtype, D, is_key ? kGroupThreadK : kGroupThreadQ, dim3((S + 127) / 128, H, B), reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sab_quant_per_block_int8_varlen(const void* x, int dtype, const void* mean, int8_t* out, float* scale,
+                                               const int32_t* cu_seqlens, const int32_t* cu_scale, int nseq,
+                                               int max_seqlen, int H, int D, int64_t x_stride_t, int64_t x_stride_h,
+                                               int64_t o_stride_t, int64_t o_stride_h, int blk, int has_sm_scale,
+                                               float sm_scale, void* stream) {
+  int st = check_common(x, dtype, D, 0, x_stride_h, x_stride_t);
+  if (st) return st;
+  SAB_REQUIRE(out && scale && cu_seqlens && cu_scale && nseq > 0 && max_seqlen > 0 && H > 0, SAB_ERR_INVALID, "bad arguments to sab_quant_per_block_int8_varlen");
+  SAB_REQUIRE(blk == 64 || blk == 128, SAB_ERR_UNSUPPORTED, "Unsupported block size: %d", blk);
+  QuantParams p{};
+  p.x = x; p.mean = mean; p.out = out; p.scale = scale; p.H = H; p.S = 0; p.scale_cols = 0;
+  p.xsh = x_stride_h; p.xss = x_stride_t; p.osh = o_stride_h; p.oss = o_stride_t;
+  p.blk = blk; p.semantics = SAB_SEM_TRITON; p.has_sm_scale = has_sm_scale; p.sm_scale = sm_scale; p.eps_after = 0;
+  p.cu = cu_seqlens; p.cu_scale = cu_scale;
+  return launch_quant(p, dtype, D, kGroupBlock, dim3((max_seqlen + 127) / 128, H, nseq), reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sab_per_channel_fp8(const void* v, int dtype, uint8_t* v_fp8, float* v_scale, float* v_mean, int B, int H,
+                                   int S, int D, int64_t stride_b, int64_t stride_h, int64_t stride_s, int64_t s_pad,
+                                   float scale_max, const int32_t* cu_seqlens, const int32_t* cu_pad, int nseq,
+                                   int max_seqlen, void* workspace, void* stream) {
+  int st = check_common(v, dtype, D, cu_seqlens ? 0 : stride_b, stride_h, stride_s);
+  if (st) return st;
+  SAB_REQUIRE(v_fp8 && v_scale && workspace && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_per_channel_fp8");
+  SAB_REQUIRE(s_pad % 128 == 0 && aligned16(v_fp8), SAB_ERR_INVALID, "s_pad must be a multiple of 128 and v_fp8 16-byte aligned");
+  const bool varlen = cu_seqlens != nullptr;
+  if (varlen) SAB_REQUIRE(cu_pad && nseq > 0 && max_seqlen > 0, SAB_ERR_INVALID, "varlen needs cu_pad, nseq, max_seqlen");
+  else SAB_REQUIRE(s_pad >= S && B > 0, SAB_ERR_INVALID, "s_pad < S");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int Bs = varlen ? 1 : B;  // statistics over all tokens of the packed batch
+  if ((st = run_stats(v, dtype, reinterpret_cast<float*>(workspace), Bs, H, S, D, varlen ? 0 : stride_b, stride_h, stride_s, s))) return st;
+  const int nchunk = (S + kStatChunk - 1) / kStatChunk;
+  float* recp = reinterpret_cast<float*>(workspace) + int64_t(Bs) * H * nchunk * 3 * D;
+  channel_stats_stage2<__half><<<Bs * H, 128, 0, s>>>(reinterpret_cast<float*>(workspace), nchunk, D, S, 1, nullptr, v_scale, v_mean, scale_max, recp);
+  SAB_CUDA_OK(cudaGetLastError());
+  VQuantParams p{};
+  p.v = v; p.out = v_fp8; p.recp = recp; p.vmean = v_mean; p.H = H; p.S = S;
+  p.sb = stride_b; p.sh = stride_h; p.ss = stride_s; p.s_pad = s_pad; p.scale_max = scale_max; p.cu = cu_seqlens; p.cu_pad = cu_pad;
+  dim3 grid(varlen ? (max_seqlen + 127) / 128 : int(s_pad / 128), H, varlen ? nseq : B);
+#define SAB_VQ(T, DD) v_quant_transpose_kernel<T, DD><<<grid, 256, 0, s>>>(p)
+  if (dtype == SAB_DTYPE_FP16) { if (D == 128) SAB_VQ(__half, 128); else SAB_VQ(__half, 64); }
+  else { if (D == 128) SAB_VQ(__nv_bfloat16, 128); else SAB_VQ(__nv_bfloat16, 64); }
+#undef SAB_VQ
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
+}
