@@ -69,7 +69,7 @@ def quant_per_block_int8_triton(x: torch.Tensor, BLK: int, sm_scale: float = 1.0
     B, H, S, D = xh.shape
     xf = _pad_seq(xh.float(), BLK) * torch.tensor(sm_scale, dtype=torch.float32)
     nblk = xf.shape[2] // BLK
-    xb = xf.view(B, H, nblk, BLK * D)
+    xb = xf.reshape(B, H, nblk, BLK * D)
     scale = xb.abs().amax(dim=-1) / 127.0
     q = _round_half_away_to_int8(xb / scale[..., None]).view(B, H, nblk * BLK, D)[:, :, :S]
     if tensor_layout == "NHD":
@@ -103,14 +103,14 @@ def quant_per_thread_int8_triton(q, k, km=None, BLKQ=128, WARPQ=32, BLKK=64, WAR
     # ---- Q
     qf = _pad_seq(qh.float(), BLKQ)
     nwq = qf.shape[2] // WARPQ
-    qg = qf.view(B, Hq, nwq, WARPQ // 8, 8, D)                  # row = w*32 + i*8 + g
+    qg = qf.reshape(B, Hq, nwq, WARPQ // 8, 8, D)                  # row = w*32 + i*8 + g
     q_scale = qg.abs().amax(dim=(3, 5)) / 127.0 + 0.0000001     # [B,H,nwq,8]
     q8 = _round_half_away_to_int8(qg / q_scale[:, :, :, None, :, None]).view(B, Hq, -1, D)[:, :, :Sq]
     q_scale = q_scale.reshape(B, Hq, nwq * 8)
     # ---- K
     kf = _pad_seq(kh.float(), BLKK)
     nwk = kf.shape[2] // WARPK
-    kg = kf.view(B, Hk, nwk, WARPK // 8, 4, 2, D)               # key = w*64 + j*8 + t*2 + e
+    kg = kf.reshape(B, Hk, nwk, WARPK // 8, 4, 2, D)               # key = w*64 + j*8 + t*2 + e
     k_scale = kg.abs().amax(dim=(3, 5, 6)) / 127.0 + 0.0000001  # [B,H,nwk,4]
     k8 = _round_half_away_to_int8(kg / k_scale[:, :, :, None, :, None, None]).view(B, Hk, -1, D)[:, :, :Sk]
     k_scale = k_scale.reshape(B, Hk, nwk * 4)
@@ -135,7 +135,7 @@ def quant_int8_cuda(x: torch.Tensor, BLK: int, mean: Optional[torch.Tensor] = No
         xf = xf * torch.tensor(sm_scale, dtype=torch.float32)
     xf = _pad_seq(xf, BLK)
     nblk = xf.shape[2] // BLK
-    xb = xf.view(B, H, nblk, BLK * D)
+    xb = xf.reshape(B, H, nblk, BLK * D)
     amax = xb.abs().amax(dim=-1).clamp_min(0.0000001)
     scale = amax / 127.0
     tmp = 127.0 / amax
