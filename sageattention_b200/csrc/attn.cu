@@ -3,25 +3,31 @@
 // One CTA = one 128-row Q tile of one (batch, head).  192 threads, warp-specialised:
 //   warps 0-3 : softmax / correction / epilogue — ONE THREAD PER Q ROW (TMEM lane == row), so row max and
 //               row sum need no shuffles and the O row a thread rescales is the row it owns
-//   warp 4    : TMA producer (Q once, K / V^T tiles through an NS-stage mbarrier ring, swizzled smem)
+//   warp 4    : TMA producer (Q once; K and V^T in 128-key stages through an NS-deep mbarrier ring, swizzled smem)
 //   warp 5    : tcgen05.mma issuer (single thread) + TMEM allocator
-// Tensor memory (256 columns per CTA, so two CTAs co-reside per SM and overlap softmax with MMA):
-//   cols [0,128)      S = Q K^T  (int32, 128x128, kind::i8)   — P (e4m3, 32 cols) is written over cols [0,32)
-//   cols [128,128+D)  O accumulator (fp32, 128xD, kind::f8f6f4, A = P from TMEM, B = V^T tile from smem)
-// Numerics follow the reference kernel csrc/qattn/qk_int_sv_f8_cuda_sm89.cuh (base-2 online softmax, the
-// -8.807 exponent offset so that P fills the e4m3 range (0,448], d accumulated from un-rounded fp32 P, mask
-// value semantics, rcp.approx / lg2.approx epilogue).  Differences, all within the stated 1e-2 tolerance:
-// the kv tile is 128 keys (reference 64) and PV accumulates in fp32 inside the tensor core across tiles.
+// The softmax / MMA tile is 64 keys — the reference's CTA_K — so the running-max sequence, P (e4m3) and d are the
+// ones csrc/qattn/qk_int_sv_f8_cuda_sm89.cuh produces.  Tensor memory, 256 columns per CTA (two CTAs per SM):
+//   cols [0,64) / [64,128)  S(j) = Q K_j^T, int32 128x64, kind::i8, DOUBLE-BUFFERED on j&1: QK(j+1), QK(j+2) run on
+//                           the tensor core while the softmax warps work on S(j); P(j) (e4m3, 16 cols) overwrites
+//                           cols [0,16) of its S buffer and is the A operand (from TMEM) of the PV MMA
+//   cols [128,128+D)        O accumulator, fp32 128xD, kind::f8f6f4, B = V^T tile from smem
+// MMA order on the in-order tensor pipe:  QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...
+// Numerics follow the reference kernel (base-2 online softmax, -8.807 exponent offset so P fills (0,448], d from
+// un-rounded fp32 P, top-left causal alignment, rcp/lg2/ex2 .approx).  The one deliberate difference: PV accumulates
+// in fp32 inside the tensor core across tiles (the reference's f16 first-level accumulator is a consumer-GPU speed
+// trick; tcgen05 f32 accumulation is full rate).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace sab {
 
 constexpr int BM = 128;  // Q rows per CTA
-constexpr int BN = 128;  // keys per kv tile
-constexpr int kNumThreads = 192;
+constexpr int BN = 64;   // keys per softmax / MMA tile (reference CTA_K)
+constexpr int LK = 128;  // keys per TMA stage (two tiles)
+constexpr int kNumThreads = 256;  // warps 0-3 softmax warpgroup; warps 4-7: TMA, MMA, 2 idle (setmaxnreg is per warpgroup)
 constexpr uint32_t kTmemCols = 256;
 constexpr float kFp8Offset = 8.807f;      // attn_utils.cuh:30
 constexpr float kMaskValue = -5000000.0f; // attn_utils.cuh:310
@@ -55,7 +61,8 @@ struct AttnParams {
 };
 
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
-  // Bounded spin: a protocol bug traps (visible as a launch failure) instead of hanging the GPU.
+#ifdef SAB_WATCHDOG
+  // Debug build: bounded spin, a protocol bug traps (visible as a launch failure) instead of hanging the GPU.
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
@@ -63,6 +70,9 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+#else
+  mbar_wait(bar, parity);
+#endif
 }
 
 template <typename T>
@@ -83,11 +93,12 @@ template <int D, bool kKT, typename OutT>
 __global__ void __launch_bounds__(kNumThreads, 2)
 sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  constexpr int NS = (D == 128) ? 2 : 4;      // K/V ring depth
+  constexpr int NS = (D == 128) ? 2 : 4;      // K/V ring depth (128-key stages)
   constexpr int SWQK = (D == 128) ? 128 : 64; // swizzle span of the Q/K tiles (= row bytes)
-  constexpr uint32_t Q_BYTES = BM * D, K_BYTES = BN * D, V_BYTES = D * BN;
-  constexpr int NG = kKT ? 8 : 2;             // dequant-scale groups per 128-key tile
-  constexpr int GPB = NG / 2;                 // groups per 64-key block
+  constexpr uint32_t Q_BYTES = BM * D, K_BYTES = LK * D, V_BYTES = D * LK;
+  constexpr uint64_t K_HALF = (uint64_t(BN) * D) >> 4;  // descriptor delta: keys 64..127 of a K stage
+  constexpr uint64_t V_HALF = uint64_t(BN) >> 4;        // descriptor delta: byte column 64 of a V^T stage
+  constexpr int NG = kKT ? 4 : 1;                       // dequant-scale groups per 64-key tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -96,10 +107,11 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sV = sK + NS * K_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * V_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* s_full = bars + 1;
-  uint64_t* p_full = bars + 2;
-  uint64_t* o_full = bars + 3;
-  uint64_t* k_full = bars + 4;
+  uint64_t* o_full = bars + 1;
+  uint64_t* pv_done = bars + 2;
+  uint64_t* s_full = bars + 3;   // [2]
+  uint64_t* p_full = bars + 5;   // [2]
+  uint64_t* k_full = bars + 7;
   uint64_t* k_empty = k_full + NS;
   uint64_t* v_full = k_empty + NS;
   uint64_t* v_empty = v_full + NS;
@@ -128,9 +140,9 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tb = 0;
     if (qt * BM >= q_len) return;  // attn_qk_int8_block_varlen.py:84-85
   }
-  int n_kv = (kv_len + BN - 1) / BN;
-  if (p.causal) n_kv = min(n_kv, qt + 1);
-  const int n_kblk = (kv_len + 63) / 64;
+  int n_kv = (kv_len + BN - 1) / BN;                 // 64-key tiles
+  if (p.causal) n_kv = min(n_kv, (qt + 1) * (BM / BN));
+  const int n_st = (n_kv + 1) / 2;                   // 128-key TMA stages
 
   // ---------------- one-time setup
   if (warp == 4 && lane == 0) {
@@ -138,9 +150,12 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
     mbar_init(o_full, 1);
+    mbar_init(pv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full + i, 1);
+      mbar_init(p_full + i, 128);
+    }
     for (int i = 0; i < NS; ++i) {
       mbar_init(k_full + i, 1);
       mbar_init(k_empty + i, 1);
@@ -154,55 +169,69 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const uint32_t tS = tmem_base;        // cols [0,128)
-  const uint32_t tP = tmem_base;        // cols [0,32) (aliases S)
-  const uint32_t tO = tmem_base + 128;  // cols [128,128+D)
+  const uint32_t tO = tmem_base + 128;  // cols [128,128+D); S buffer b at cols [64b, 64b+64), P(b) at its first 16
 
-  if (warp == 4) {
+  if (warp >= 4) {
+    setmaxnreg_dec_48();
+    if (warp == 4) {
     // =============================== TMA producer ===============================
     if (lane == 0 && n_kv > 0) {
       mbar_expect_tx(q_full, Q_BYTES);
       tma_load_4d(sQ, &tmQ, q_full, 0, q_off + qt * BM, h, tb);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % NS;
-        const uint32_t ph = (j / NS) & 1;
+      for (int jj = 0; jj < n_st; ++jj) {
+        const int s = jj % NS;
+        const uint32_t ph = (jj / NS) & 1;
         mbar_wait_wd(k_empty + s, ph ^ 1);
         mbar_expect_tx(k_full + s, K_BYTES);
-        tma_load_4d(sK + s * K_BYTES, &tmK, k_full + s, 0, k_off + j * BN, hk, tb);
+        tma_load_4d(sK + s * K_BYTES, &tmK, k_full + s, 0, k_off + jj * LK, hk, tb);
         mbar_wait_wd(v_empty + s, ph ^ 1);
         mbar_expect_tx(v_full + s, V_BYTES);
-        tma_load_4d(sV + s * V_BYTES, &tmV, v_full + s, v_off + j * BN, 0, hk, tb);
+        tma_load_4d(sV + s * V_BYTES, &tmV, v_full + s, v_off + jj * LK, 0, hk, tb);
       }
     }
-  } else if (warp == 5) {
+    } else if (warp == 5) {
     // =============================== MMA issuer ===============================
     if (lane == 0 && n_kv > 0) {
-      constexpr uint32_t idesc_qk = make_idesc(2, 1, 1, BM, BN);  // s32 <- s8 x s8
-      constexpr uint32_t idesc_pv = make_idesc(1, 0, 0, BM, D);   // f32 <- e4m3 x e4m3
+      constexpr uint32_t idesc_qk = make_idesc(2, 1, 1, BM, BN);  // s32 <- s8 x s8, 128 x 64
+      constexpr uint32_t idesc_pv = make_idesc(1, 0, 0, BM, D);   // f32 <- e4m3 x e4m3, 128 x D
       const uint64_t dQ = make_smem_desc<SWQK>(smem_u32(sQ));
-      mbar_wait_wd(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % NS;
-        const uint32_t ph = (j / NS) & 1;
-        mbar_wait_wd(k_full + s, ph);
-        tc_fence_after();
-        const uint64_t dK = make_smem_desc<SWQK>(smem_u32(sK + s * K_BYTES));
+      auto issue_qk = [&](int j) {
+        const int jj = j >> 1, s = jj % NS, half = j & 1;
+        if (half == 0) {
+          mbar_wait_wd(k_full + s, (jj / NS) & 1);
+          tc_fence_after();
+        }
+        const uint64_t dK = make_smem_desc<SWQK>(smem_u32(sK + s * K_BYTES)) + half * K_HALF;
+        const uint32_t tS = tmem_base + (j & 1) * BN;
 #pragma unroll
         for (int k = 0; k < D / 32; ++k) umma_i8_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_qk, k > 0);
-        tc_commit(k_empty + s);  // K stage reusable once the MMAs retire
-        tc_commit(s_full);       // S(j) ready (also implies PV(j-1) retired: in-order pipe)
-        mbar_wait_wd(p_full, j & 1);
+        if (half == 1 || j == n_kv - 1) tc_commit(k_empty + s);  // K stage reusable once its MMAs retire
+        tc_commit(s_full + (j & 1));
+      };
+      mbar_wait_wd(q_full, 0);
+      issue_qk(0);
+      if (n_kv > 1) issue_qk(1);
+      for (int j = 0; j < n_kv; ++j) {
+        const int jj = j >> 1, s = jj % NS, half = j & 1;
+        mbar_wait_wd(p_full + (j & 1), (j >> 1) & 1);   // P(j) stored by all 128 rows (also: S(j) fully consumed)
         tc_fence_after();
-        mbar_wait_wd(v_full + s, ph);
-        tc_fence_after();
-        const uint64_t dV = make_smem_desc<128>(smem_u32(sV + s * V_BYTES));
+        if (half == 0) {
+          mbar_wait_wd(v_full + s, (jj / NS) & 1);
+          tc_fence_after();
+        }
+        const uint64_t dV = make_smem_desc<128>(smem_u32(sV + s * V_BYTES)) + half * V_HALF;
+        const uint32_t tP = tmem_base + (j & 1) * BN;
 #pragma unroll
         for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tO, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
-        tc_commit(v_empty + s);
+        if (half == 1 || j == n_kv - 1) tc_commit(v_empty + s);
+        tc_commit(pv_done);                              // phase j: O holds tiles 0..j
+        if (j + 2 < n_kv) issue_qk(j + 2);               // reuses S buffer j&1 (after PV(j): in-order pipe)
       }
       tc_commit(o_full);
     }
+    }
   } else {
+    setmaxnreg_inc_208();
     // =============================== softmax / correction / epilogue ===============================
     const int row = warp * 32 + lane;  // TMEM lane == Q row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
@@ -221,119 +250,114 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     float d = 0.f;         // running sum of fp32 P
 
     for (int j = 0; j < n_kv; ++j) {
-      // dequant coefficient per scale group of this tile (…sm89.cuh:116-132, 255-257)
+      const uint32_t tS = tmem_base + lane_off + (j & 1) * BN;
+      // dequant coefficient per scale group of this tile (…sm89.cuh:116-132, 255-257); tile j == 64-key block j
       float coef[NG];
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const int blk = 2 * j + g / GPB;
-        float ks = 0.f;
-        if (blk < n_kblk) ks = ks_base[int64_t((k_blk0 + blk) * GPB + g % GPB) * p.ks_stride_idx];
-        coef[g] = ks * qss;
-      }
+      for (int g = 0; g < NG; ++g) coef[g] = ks_base[int64_t((k_blk0 + j) * NG + g) * p.ks_stride_idx] * qss;
       // number of visible keys of this tile for this row (OOB + causal, attn_utils.cuh:296-351)
       int limit = kv_len - j * BN;
       if (p.causal) limit = min(limit, q_row - j * BN + 1);
-      const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && j >= qt);
+      const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && (j + 1) * BN > qt * BM + 1);
 
-      mbar_wait_wd(s_full, j & 1);
+      mbar_wait_wd(s_full + (j & 1), (j >> 1) & 1);
       tc_fence_after();
-
-      // ---- pass 1: row max.  Scales are positive, so max_c(S_c*coef_g(c)) = max_g(coef_g * max_{c in g} S_c):
-      //      integer max per scale group, 8 (or 2) int->float conversions per row instead of 128.
-      int gmax[NG];
-#pragma unroll
-      for (int g = 0; g < NG; ++g) gmax[g] = kIntSentinel;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_off + ch * 32, r);
+      uint32_t s[BN];
+      {
+        uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
+        uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
+        tmem_ld32(tS, lo);
+        tmem_ld32(tS + 32, hi);
         tc_wait_ld();
-        if (dump && j == 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) p.dbg[row * 128 + ch * 32 + i] = int(r[i]);
-        }
-        if (masked_tile) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (ch * 32 + i >= limit) r[i] = uint32_t(kIntSentinel);
-        }
-        if constexpr (kKT) {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            int v = gmax[(ch / 2) * 4 + t];
-#pragma unroll
-            for (int i8 = 0; i8 < 32; i8 += 8) v = __vimax3_s32(v, int(r[i8 + 2 * t]), int(r[i8 + 2 * t + 1]));
-            gmax[(ch / 2) * 4 + t] = v;
-          }
-        } else {
-          int v = gmax[ch / 2];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) v = __vimax3_s32(v, int(r[i]), int(r[i + 1]));
-          gmax[ch / 2] = v;
-        }
       }
-      float mx = kMaskValue;
+      if (dump && j == 0) {
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const float c = (gmax[g] == kIntSentinel) ? kMaskValue : float(gmax[g]) * coef[g];
-        mx = fmaxf(mx, c);
+        for (int i = 0; i < BN; ++i) p.dbg[row * BN + i] = int(s[i]);
       }
-      const float m_new = fmaxf(m, mx - kFp8Offset);  // update_mdo, attn_utils.cuh:377-396
-      const float alpha = ex2_approx(m - m_new);
-      d *= alpha;
 
-      // ---- correction: rescale this row of O (in TMEM).  PV(j-1) has retired (s_full(j) ordering).
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+      auto tile = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        // ---- row max.  Scales are positive, so max_c(S_c*coef_g(c)) = max_g(coef_g * max_{c in g} S_c): integer
+        //      max per scale group (DPX 3-input max), one int->float conversion per group instead of per element.
+        if constexpr (MASKED) {
 #pragma unroll
-        for (int ch = 0; ch < D / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld32(tO + lane_off + ch * 32, r);
+          for (int i = 0; i < BN; ++i)
+            if (i >= limit) s[i] = uint32_t(kIntSentinel);
+        }
+        float mx = kMaskValue;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          int v = kIntSentinel;
+          if constexpr (kKT) {
+#pragma unroll
+            for (int i8 = 0; i8 < BN; i8 += 8) v = __vimax3_s32(v, int(s[i8 + 2 * g]), int(s[i8 + 2 * g + 1]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN; i += 2) v = __vimax3_s32(v, int(s[i]), int(s[i + 1]));
+          }
+          float c = float(v) * coef[g];
+          if constexpr (MASKED) c = (v == kIntSentinel) ? kMaskValue : c;
+          mx = fmaxf(mx, c);
+        }
+        const float m_new = fmaxf(m, mx - kFp8Offset);  // update_mdo, attn_utils.cuh:377-396
+        const float alpha = ex2_approx(m - m_new);
+        d *= alpha;
+        m = m_new;
+
+        // ---- P = exp2(S*coef - m_new) -> e4m3 into TMEM (over the S buffer), d += sum(P)
+        // int32 -> fp32 through the 1.5*2^23 magic constant (exact for |S| < 2^22); its bias is folded into the
+        // FMA addend, so the dequant + max-subtract + conversion is ONE FFMA per element.
+        float nb[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) nb[g] = fmaf(-12582912.0f, coef[g], -m_new);
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        uint32_t pk[BN / 4];
+#pragma unroll
+        for (int w = 0; w < BN / 4; ++w) {
+          float e[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = 4 * w + u;
+            const int g = kKT ? ((i & 7) >> 1) : 0;
+            const float f = __uint_as_float(s[i] + 0x4B400000u);
+            e[u] = ex2_approx(fmaf(f, coef[g], nb[g]));
+            if constexpr (MASKED) e[u] = (i < limit) ? e[u] : 0.f;
+          }
+          acc0 += e[0];
+          acc1 += e[1];
+          acc2 += e[2];
+          acc3 += e[3];
+          pk[w] = pack_e4m3x4(e[0], e[1], e[2], e[3]);
+        }
+        d += (acc0 + acc1) + (acc2 + acc3);
+        tmem_st16(tS, pk);
+        // ---- correction: rescale this row of O (in TMEM).  Done AFTER the exponentials so that the wait for PV(j-1)
+        //      is hidden behind ~350 instructions of softmax work; PV(j) cannot start before p_full(j) below.
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+          mbar_wait_wd(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          uint32_t r[D / 32][32];
+#pragma unroll
+          for (int ch = 0; ch < D / 32; ++ch) tmem_ld32(tO + lane_off + ch * 32, r[ch]);
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st32(tO + lane_off + ch * 32, r);
+          for (int ch = 0; ch < D / 32; ++ch) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[ch][i] = __float_as_uint(__uint_as_float(r[ch][i]) * alpha);
+            tmem_st32(tO + lane_off + ch * 32, r[ch]);
+          }
         }
-      }
-
-      // ---- pass 2: P = exp2(S*coef - m_new) -> e4m3 into TMEM (over S), d += sum(P)
-      const float nm = -m_new;
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_off + ch * 32, r);
-        tc_wait_ld();
-        float pf[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          // exact int32 -> fp32 for |S| < 2^22 via the 1.5*2^23 magic constant (no I2F on the slow pipe)
-          const float sf = __uint_as_float(r[i] + 0x4B400000u) - 12582912.0f;
-          const int g = (ch / 2) * GPB + (kKT ? ((i & 7) >> 1) : 0);
-          float e = ex2_approx(fmaf(sf, coef[g], nm));
-          if (masked_tile && (ch * 32 + i >= limit)) e = 0.f;
-          pf[i] = e;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          acc0 += pf[i];
-          acc1 += pf[i + 1];
-          acc2 += pf[i + 2];
-          acc3 += pf[i + 3];
-        }
-        uint32_t pk[8];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) pk[w] = pack_e4m3x4(pf[4 * w], pf[4 * w + 1], pf[4 * w + 2], pf[4 * w + 3]);
-        tmem_st8(tP + lane_off + ch * 8, pk);
         if (dump && j == 0) {
 #pragma unroll
-          for (int w = 0; w < 8; ++w) p.dbg[128 * 128 + row * 32 + ch * 8 + w] = int(pk[w]);
+          for (int w = 0; w < BN / 4; ++w) p.dbg[128 * BN + row * 16 + w] = int(pk[w]);
         }
-      }
-      d += (acc0 + acc1) + (acc2 + acc3);
-      m = m_new;
+      };
+      if (masked_tile) tile(std::true_type{});
+      else tile(std::false_type{});
+
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(p_full + (j & 1));
     }
 
     // ---- epilogue: O / d * v_scale (+ v_mean) -> fp16/bf16, 16-byte stores (…sm89.cuh:572-703)
@@ -353,7 +377,7 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_wait_ld();
         if (dump) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) p.dbg[128 * 128 + 128 * 32 + row * D + ch * 32 + i] = int(r[i]);
+          for (int i = 0; i < 32; ++i) p.dbg[128 * BN + 128 * 16 + row * D + ch * 32 + i] = int(r[i]);
         }
         uint32_t o16[16];
 #pragma unroll
@@ -376,8 +400,8 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       if (dump) {
-        p.dbg[128 * 128 + 128 * 32 + 128 * D + row] = __float_as_int(d);
-        p.dbg[128 * 128 + 128 * 32 + 128 * D + 128 + row] = __float_as_int(m);
+        p.dbg[128 * BN + 128 * 16 + 128 * D + row] = __float_as_int(d);
+        p.dbg[128 * BN + 128 * 16 + 128 * D + 128 + row] = __float_as_int(m);
       }
     } else if (row_ok) {
       uint4* dst = reinterpret_cast<uint4*>(orow);
@@ -440,7 +464,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
                        dim3 grid, cudaStream_t stream) {
   constexpr int NS = (D == 128) ? 2 : 4;
   // 1 KB alignment slack + tiles + barriers; at least 80 KB so that exactly two CTAs (2 x 256 TMEM columns) fit an SM
-  size_t smem = 1024 + size_t(BM) * D + size_t(NS) * 2 * BN * D + 256;
+  size_t smem = 1024 + size_t(BM) * D + size_t(NS) * 2 * LK * D + 256;
   if (smem < 80 * 1024) smem = 80 * 1024;
   auto kern = sage_attn_fwd_kernel<D, kKT, OutT>;
   static bool configured = false;
@@ -484,13 +508,13 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
   const int swqk = D == 128 ? 128 : 64;
   if (!varlen) {
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, B, q_stride_s, q_stride_h, q_stride_b, D, BM, swqk))) return st;
-    if ((st = make_map_u8(&tk, k_int8, D, Skv > 0 ? Skv : 1, Hkv, B, k_stride_s, k_stride_h, k_stride_b, D, BN, swqk))) return st;
-    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, B, v_s_pad, uint64_t(v_s_pad) * D, uint64_t(v_s_pad) * D * Hkv, BN, D, 128))) return st;
+    if ((st = make_map_u8(&tk, k_int8, D, Skv > 0 ? Skv : 1, Hkv, B, k_stride_s, k_stride_h, k_stride_b, D, LK, swqk))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, B, v_s_pad, uint64_t(v_s_pad) * D, uint64_t(v_s_pad) * D * Hkv, LK, D, 128))) return st;
   } else {
     // packed [T,H,D]: Sq / Skv are the TOTAL token counts
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, 1, q_stride_s, q_stride_h, 0, D, BM, swqk))) return st;
-    if ((st = make_map_u8(&tk, k_int8, D, Skv, Hkv, 1, k_stride_s, k_stride_h, 0, D, BN, swqk))) return st;
-    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, 1, v_s_pad, uint64_t(v_s_pad) * D, 0, BN, D, 128))) return st;
+    if ((st = make_map_u8(&tk, k_int8, D, Skv, Hkv, 1, k_stride_s, k_stride_h, 0, D, LK, swqk))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, 1, v_s_pad, uint64_t(v_s_pad) * D, 0, LK, D, 128))) return st;
   }
 
   AttnParams p{};

@@ -39,10 +39,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+// Blocking wait: try_wait suspends the thread in hardware (up to the hint, in ns) and wakes it when the phase
+// completes, so a waiting warp does not burn issue slots of its SM sub-partition.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 1000000u) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "SAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra SAB_DONE;\n\t"
+      "bra SAB_WAIT;\n\t"
+      "SAB_DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
 }
+__device__ __forceinline__ void setmaxnreg_inc_208() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;"); }
+__device__ __forceinline__ void setmaxnreg_dec_48() { asm volatile("setmaxnreg.dec.sync.aligned.u32 48;"); }
 
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -115,6 +126,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
       ::SAB_W4(r, 0), SAB_W4(r, 4), SAB_W4(r, 8), SAB_W4(r, 12), SAB_W4(r, 16), SAB_W4(r, 20), SAB_W4(r, 24),
       SAB_W4(r, 28), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+      ::SAB_W4(r, 0), SAB_W4(r, 4), SAB_W4(r, 8), SAB_W4(r, 12), "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
