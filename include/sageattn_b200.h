@@ -131,6 +131,20 @@ int sab_per_channel_fp8(const void* v, int dtype, uint8_t* v_fp8, float* v_scale
                         const int32_t* cu_pad, int nseq, int max_seqlen, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Building blocks of the sequence-parallel path (no reference counterpart: the reference ships no SP
+ * code; semantics chosen so that the sharded result equals the single-GPU one):
+ *  sab_channel_stats   : per-(b,h,d) fp32 sum / max / min over the LOCAL tokens (all-reduced by the host:
+ *                        SUM for the global K mean, MAX/MIN for the global per-channel V range).
+ *  sab_v_quant_with_amax: sab_per_channel_fp8 with the per-channel |max| supplied by the caller.
+ * ---------------------------------------------------------------------------------------------- */
+int sab_channel_stats(const void* x, int dtype, float* sum_out, float* max_out, float* min_out, int B, int H,
+                      int S, int D, int64_t stride_b, int64_t stride_h, int64_t stride_s, void* workspace,
+                      void* stream);
+int sab_v_quant_with_amax(const void* v, int dtype, uint8_t* v_fp8, const float* amax, float* v_scale, int B,
+                          int H, int S, int D, int64_t stride_b, int64_t stride_h, int64_t stride_s,
+                          int64_t s_pad, float scale_max, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused attention: INT8 QK^T (tcgen05 kind::i8) -> fp32 online softmax -> FP8 P -> FP8 PV
  * (tcgen05 kind::f8f6f4, fp32 accumulation in tensor memory) -> fp16/bf16 O.
  * Replaces qk_int8_sv_f8_accum_{f32,f16}[_fuse_v_scale][_fuse_v_mean]_attn[_inst_buf]
@@ -145,6 +159,11 @@ int sab_per_channel_fp8(const void* v, int dtype, uint8_t* v_fp8, float* v_scale
  *   sm_scale: softmax scale; the kernel multiplies by log2(e) itself.  Pass fold_sm_scale != 0 when
  *            sm_scale*log2e is already folded into q (per_block Triton path, core.py:304).
  *   is_causal: top-left aligned (kv_idx > q_idx masked, attn_utils.cuh:310).
+ * Sequence-parallel form (kv_seg_len > 0, dense only): k_int8 is [P*B,Hkv,kv_seg_len,D] and v_fp8 is
+ * [P*B,Hkv,D,kv_seg_len] exactly as an all-gather of the P ranks' local shards lays them out (rank-major);
+ * key t of batch b lives in segment t / kv_seg_len.  Skv = P*kv_seg_len, kv_seg_len % 128 == 0.
+ * causal_q_offset: global index of this call's first query row (top-left causal alignment on global
+ * indices); 0 on a single GPU.
  * Varlen form (cu_seqlens_q != NULL): q/out packed [Tq,Hq,D], k packed [Tk,Hkv,D] (B = number of
  * sequences, *_stride_b ignored), v_fp8 [Hkv,D,T_pad] with cu_pad_v offsets, scales
  * [nblocks_total,H] with cu_*_scale offsets (quant_per_block_varlen.py:72-79), per_block only.
@@ -158,7 +177,8 @@ int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8, const uin
                            int q_gran, int k_gran, float sm_scale, int fold_sm_scale,
                            const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
                            const int32_t* cu_pad_v, const int32_t* cu_q_scale, const int32_t* cu_k_scale,
-                           int max_seqlen_q, int32_t* debug_dump, void* stream);
+                           int max_seqlen_q, int causal_q_offset, int kv_seg_len, int32_t* debug_dump,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -353,8 +353,9 @@ def _pad_head_dim(q, k, v):
 def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout="HND", is_causal=False,
                                  qk_quant_gran="per_thread", sm_scale=None,
                                  pv_accum_dtype="fp32+fp16", smooth_k=True, smooth_v=False,
-                                 return_lse=False, kv_tile=64):
-    """sageattention/core.py:636-826 end to end (CPU)."""
+                                 return_lse=False, kv_tile=64, emulate_f16_accum=True):
+    """sageattention/core.py:636-826 end to end (CPU).  emulate_f16_accum=False keeps the reference's V range
+    for "fp32+fp16" (2.25) but accumulates PV in fp32 — the B200 kernel's arithmetic (tcgen05 f32 accumulation)."""
     dtype = q.dtype
     q, k, v, hd_og = _pad_head_dim(q, k, v)
     if sm_scale is None:
@@ -376,8 +377,8 @@ def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout="HND", is_causal=False,
     v8, vs, _ = per_channel_fp8_cuda(v, tensor_layout, scale_max, smooth_v=False)
     o = attn_int8_fp8_cuda(_to_hnd(q8, tensor_layout), _to_hnd(k8, tensor_layout), v8, qs, ks, vs,
                            qk_quant_gran=qk_quant_gran, is_causal=is_causal, sm_scale=sm_scale,
-                           pv_accum_dtype=pv_accum_dtype, out_dtype=dtype, kv_tile=kv_tile,
-                           return_lse=return_lse)
+                           pv_accum_dtype=pv_accum_dtype if emulate_f16_accum else "fp32+fp32", out_dtype=dtype,
+                           kv_tile=kv_tile, return_lse=return_lse)
     lse = None
     if return_lse:
         o, lse = o

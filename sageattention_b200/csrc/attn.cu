@@ -57,6 +57,8 @@ struct AttnParams {
   const int32_t* cu_v;
   const int32_t* cu_qs;
   const int32_t* cu_ks;
+  int causal_q_offset;   // global index of query row 0 (sequence-parallel causal)
+  int kv_seg_len;        // > 0: K/V are rank-major all-gathered segments of this many keys
   int32_t* dbg;          // nullable debug dump (CTA 0 only)
 };
 
@@ -141,7 +143,7 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (qt * BM >= q_len) return;  // attn_qk_int8_block_varlen.py:84-85
   }
   int n_kv = (kv_len + BN - 1) / BN;                 // 64-key tiles
-  if (p.causal) n_kv = min(n_kv, (qt + 1) * (BM / BN));
+  if (p.causal) n_kv = min(n_kv, (p.causal_q_offset + (qt + 1) * BM + BN - 1) / BN);
   const int n_st = (n_kv + 1) / 2;                   // 128-key TMA stages
 
   // ---------------- one-time setup
@@ -181,12 +183,18 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int jj = 0; jj < n_st; ++jj) {
         const int s = jj % NS;
         const uint32_t ph = (jj / NS) & 1;
+        int kc = k_off + jj * LK, vc = v_off + jj * LK, kb = tb;
+        if (p.kv_seg_len > 0) {  // all-gathered layout: segment-major
+          const int seg = (jj * LK) / p.kv_seg_len;
+          kc = vc = jj * LK - seg * p.kv_seg_len;
+          kb = seg * p.B + b;
+        }
         mbar_wait_wd(k_empty + s, ph ^ 1);
         mbar_expect_tx(k_full + s, K_BYTES);
-        tma_load_4d(sK + s * K_BYTES, &tmK, k_full + s, 0, k_off + jj * LK, hk, tb);
+        tma_load_4d(sK + s * K_BYTES, &tmK, k_full + s, 0, kc, hk, kb);
         mbar_wait_wd(v_empty + s, ph ^ 1);
         mbar_expect_tx(v_full + s, V_BYTES);
-        tma_load_4d(sV + s * V_BYTES, &tmV, v_full + s, v_off + jj * LK, 0, hk, tb);
+        tma_load_4d(sV + s * V_BYTES, &tmV, v_full + s, vc, 0, hk, kb);
       }
     }
     } else if (warp == 5) {
@@ -257,8 +265,8 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int g = 0; g < NG; ++g) coef[g] = ks_base[int64_t((k_blk0 + j) * NG + g) * p.ks_stride_idx] * qss;
       // number of visible keys of this tile for this row (OOB + causal, attn_utils.cuh:296-351)
       int limit = kv_len - j * BN;
-      if (p.causal) limit = min(limit, q_row - j * BN + 1);
-      const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && (j + 1) * BN > qt * BM + 1);
+      if (p.causal) limit = min(limit, p.causal_q_offset + q_row - j * BN + 1);
+      const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && (j + 1) * BN > p.causal_q_offset + qt * BM + 1);
 
       mbar_wait_wd(s_full + (j & 1), (j >> 1) & 1);
       tc_fence_after();
@@ -488,7 +496,8 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
                                       int q_gran, int k_gran, float sm_scale, int fold_sm_scale,
                                       const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
                                       const int32_t* cu_pad_v, const int32_t* cu_q_scale, const int32_t* cu_k_scale,
-                                      int max_seqlen_q, int32_t* debug_dump, void* stream) {
+                                      int max_seqlen_q, int causal_q_offset, int kv_seg_len, int32_t* debug_dump,
+                                      void* stream) {
   using namespace sab;
   SAB_REQUIRE(q_int8 && k_int8 && v_fp8 && out && q_scale && k_scale, SAB_ERR_INVALID, "null tensor pointer");
   SAB_REQUIRE(D == 64 || D == 128, SAB_ERR_UNSUPPORTED, "Unsupported head dim: %d (64 or 128 after padding)", D);
@@ -496,9 +505,13 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
   SAB_REQUIRE(B > 0 && Hq > 0 && Hkv > 0 && Sq > 0 && Skv >= 0, SAB_ERR_INVALID, "bad sizes B=%d Hq=%d Hkv=%d Sq=%d Skv=%d", B, Hq, Hkv, Sq, Skv);
   SAB_REQUIRE(Hq % Hkv == 0, SAB_ERR_INVALID, "num_qo_heads (%d) must be divisible by num_kv_heads (%d)", Hq, Hkv);
   SAB_REQUIRE(q_gran >= 1 && q_gran <= 3 && k_gran >= 1 && k_gran <= 3, SAB_ERR_INVALID, "unknown quant granularity q=%d k=%d", q_gran, k_gran);
-  SAB_REQUIRE(v_s_pad % 128 == 0 && v_s_pad >= Skv, SAB_ERR_INVALID, "v_fp8 token dimension (%lld) must be a multiple of 128 and >= kv_len", (long long)v_s_pad);
+  SAB_REQUIRE(v_s_pad % 128 == 0 && (v_s_pad >= Skv || kv_seg_len > 0), SAB_ERR_INVALID, "v_fp8 token dimension (%lld) must be a multiple of 128 and >= kv_len", (long long)v_s_pad);
   SAB_REQUIRE(aligned16(out) && o_stride_s % 8 == 0 && o_stride_h % 8 == 0 && o_stride_b % 8 == 0, SAB_ERR_INVALID, "output must be 16-byte aligned with strides multiple of 8 elements");
   const bool varlen = cu_seqlens_q != nullptr;
+  SAB_REQUIRE(causal_q_offset >= 0 && kv_seg_len >= 0, SAB_ERR_INVALID, "negative causal_q_offset / kv_seg_len");
+  if (kv_seg_len > 0)
+    SAB_REQUIRE(!varlen && kv_seg_len % 128 == 0 && Skv % kv_seg_len == 0 && v_s_pad == kv_seg_len, SAB_ERR_INVALID,
+                "sequence-parallel form needs dense tensors, kv_seg_len %% 128 == 0, Skv %% kv_seg_len == 0, v_s_pad == kv_seg_len");
   if (varlen)
     SAB_REQUIRE(cu_seqlens_k && cu_pad_v && cu_q_scale && cu_k_scale && max_seqlen_q > 0, SAB_ERR_INVALID, "varlen needs cu_seqlens_k, cu_pad_v, cu_q_scale, cu_k_scale and max_seqlen_q");
   int st = sab_check_device();
@@ -506,7 +519,12 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
 
   CUtensorMap tq, tk, tv;
   const int swqk = D == 128 ? 128 : 64;
-  if (!varlen) {
+  if (kv_seg_len > 0) {
+    const int P = Skv / kv_seg_len;
+    if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, B, q_stride_s, q_stride_h, q_stride_b, D, BM, swqk))) return st;
+    if ((st = make_map_u8(&tk, k_int8, D, kv_seg_len, Hkv, uint64_t(B) * P, k_stride_s, k_stride_h, k_stride_b, D, LK, swqk))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, uint64_t(B) * P, v_s_pad, uint64_t(v_s_pad) * D, uint64_t(v_s_pad) * D * Hkv, LK, D, 128))) return st;
+  } else if (!varlen) {
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, B, q_stride_s, q_stride_h, q_stride_b, D, BM, swqk))) return st;
     if ((st = make_map_u8(&tk, k_int8, D, Skv > 0 ? Skv : 1, Hkv, B, k_stride_s, k_stride_h, k_stride_b, D, LK, swqk))) return st;
     if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, B, v_s_pad, uint64_t(v_s_pad) * D, uint64_t(v_s_pad) * D * Hkv, LK, D, 128))) return st;
@@ -534,6 +552,7 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
   p.qs_stride_idx = varlen ? Hq : 1;
   p.ks_stride_idx = varlen ? Hkv : 1;
   p.cu_q = cu_seqlens_q; p.cu_k = cu_seqlens_k; p.cu_v = cu_pad_v; p.cu_qs = cu_q_scale; p.cu_ks = cu_k_scale;
+  p.causal_q_offset = causal_q_offset; p.kv_seg_len = kv_seg_len;
   p.dbg = debug_dump;
 
   dim3 grid(p.n_q_tiles, Hq, B);

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) channel_stats_stage1(const T* __restrict_
   }
 }
 
-// mode 0: K mean -> T [B,H,D].  mode 1: V scale (+ mean) -> fp32.
+// mode 0: K mean -> T [B,H,D].  mode 1: V scale (+ mean) -> fp32.  mode 2: raw sum / max / min -> fp32.
 template <typename T>
 __global__ void channel_stats_stage2(const float* __restrict__ part, int nchunk, int D, int S, int mode, T* mean_out,
                                      float* scale_out, float* vmean_out, float scale_max, float* recp_out) {
@@ -93,7 +93,11 @@ __global__ void channel_stats_stage2(const float* __restrict__ part, int nchunk,
   const float* p = part + int64_t(bh) * nchunk * 3 * D;
   float a = 0.f, m1 = -INFINITY, m2 = INFINITY;
   for (int c = 0; c < nchunk; ++c) { a += p[c * 3 * D + d]; m1 = fmaxf(m1, p[c * 3 * D + D + d]); m2 = fminf(m2, p[c * 3 * D + 2 * D + d]); }
-  if (mode == 0) {
+  if (mode == 2) {
+    scale_out[int64_t(bh) * D + d] = a;
+    vmean_out[int64_t(bh) * D + d] = m1;
+    recp_out[int64_t(bh) * D + d] = m2;
+  } else if (mode == 0) {
     mean_out[int64_t(bh) * D + d] = from_f<T>(__fdiv_rn(a, float(S)));  // torch.mean: fp32 sum / N, cast
   } else {
     float amax;
@@ -454,6 +458,54 @@ extern "C" int sab_per_channel_fp8(const void* v, int dtype, uint8_t* v_fp8, flo
   p.v = v; p.out = v_fp8; p.recp = recp; p.vmean = v_mean; p.H = H; p.S = S;
   p.sb = stride_b; p.sh = stride_h; p.ss = stride_s; p.s_pad = s_pad; p.scale_max = scale_max; p.cu = cu_seqlens; p.cu_pad = cu_pad;
   dim3 grid(varlen ? (max_seqlen + 127) / 128 : int(s_pad / 128), H, varlen ? nseq : B);
+#define SAB_VQ(T, DD) v_quant_transpose_kernel<T, DD><<<grid, 256, 0, s>>>(p)
+  if (dtype == SAB_DTYPE_FP16) { if (D == 128) SAB_VQ(__half, 128); else SAB_VQ(__half, 64); }
+  else { if (D == 128) SAB_VQ(__nv_bfloat16, 128); else SAB_VQ(__nv_bfloat16, 64); }
+#undef SAB_VQ
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
+}
+
+__global__ void amax_to_scale_kernel(const float* __restrict__ amax, float* __restrict__ scale, float* __restrict__ recp,
+                                     int n, float scale_max) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float a = amax[i];
+    scale[i] = __fdividef(a, scale_max);
+    recp[i] = a > 0.f ? __fdividef(scale_max, a) : 0.f;
+  }
+}
+
+extern "C" int sab_channel_stats(const void* x, int dtype, float* sum_out, float* max_out, float* min_out, int B, int H,
+                                 int S, int D, int64_t stride_b, int64_t stride_h, int64_t stride_s, void* workspace,
+                                 void* stream) {
+  int st = check_common(x, dtype, D, stride_b, stride_h, stride_s);
+  if (st) return st;
+  SAB_REQUIRE(sum_out && max_out && min_out && workspace && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_channel_stats");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if ((st = run_stats(x, dtype, reinterpret_cast<float*>(workspace), B, H, S, D, stride_b, stride_h, stride_s, s))) return st;
+  const int nchunk = (S + kStatChunk - 1) / kStatChunk;
+  channel_stats_stage2<__half><<<B * H, 128, 0, s>>>(reinterpret_cast<float*>(workspace), nchunk, D, S, 2, nullptr, sum_out, max_out, 0.f, min_out);
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
+}
+
+extern "C" int sab_v_quant_with_amax(const void* v, int dtype, uint8_t* v_fp8, const float* amax, float* v_scale, int B,
+                                     int H, int S, int D, int64_t stride_b, int64_t stride_h, int64_t stride_s,
+                                     int64_t s_pad, float scale_max, void* workspace, void* stream) {
+  int st = check_common(v, dtype, D, stride_b, stride_h, stride_s);
+  if (st) return st;
+  SAB_REQUIRE(v_fp8 && amax && v_scale && workspace && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_v_quant_with_amax");
+  SAB_REQUIRE(s_pad % 128 == 0 && s_pad >= S && aligned16(v_fp8), SAB_ERR_INVALID, "s_pad must be a multiple of 128, >= S, v_fp8 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* recp = reinterpret_cast<float*>(workspace);   // B*H*D floats
+  const int n = B * H * D;
+  amax_to_scale_kernel<<<(n + 255) / 256, 256, 0, s>>>(amax, v_scale, recp, n, scale_max);
+  SAB_CUDA_OK(cudaGetLastError());
+  VQuantParams p{};
+  p.v = v; p.out = v_fp8; p.recp = recp; p.vmean = nullptr; p.H = H; p.S = S;
+  p.sb = stride_b; p.sh = stride_h; p.ss = stride_s; p.s_pad = s_pad; p.scale_max = scale_max; p.cu = nullptr; p.cu_pad = nullptr;
+  dim3 grid(int(s_pad / 128), H, B);
 #define SAB_VQ(T, DD) v_quant_transpose_kernel<T, DD><<<grid, 256, 0, s>>>(p)
   if (dtype == SAB_DTYPE_FP16) { if (D == 128) SAB_VQ(__half, 128); else SAB_VQ(__half, 64); }
   else { if (D == 128) SAB_VQ(__nv_bfloat16, 128); else SAB_VQ(__nv_bfloat16, 64); }

@@ -138,16 +138,53 @@ def _(v, v_fp8, v_scale, cu_seqlens, cu_pad, max_seqlen, scale_max):
     return None
 
 
+# ----------------------------------------------------------------------------------------------- SP building blocks
+@torch.library.custom_op("sageattention_b200::channel_stats", mutates_args=("sum_out", "max_out", "min_out"), device_types="cuda")
+def channel_stats(x: torch.Tensor, sum_out: torch.Tensor, max_out: torch.Tensor, min_out: torch.Tensor, tensor_layout: int) -> None:
+    B, H, S, D = _bhsd(x, tensor_layout)
+    sb, sh, ss = _bhs_strides(x, tensor_layout)
+    with torch.cuda.device(x.device):
+        ws = torch.empty(lib().sab_k_mean_workspace_bytes(B, H, S, D), dtype=torch.uint8, device=x.device)
+        check(lib().sab_channel_stats(x.data_ptr(), _dt(x), sum_out.data_ptr(), max_out.data_ptr(), min_out.data_ptr(),
+                                      B, H, S, D, sb, sh, ss, ws.data_ptr(), _stream(x)))
+
+
+@channel_stats.register_fake
+def _(x, sum_out, max_out, min_out, tensor_layout):
+    return None
+
+
+@torch.library.custom_op("sageattention_b200::v_quant_with_amax", mutates_args=("v_fp8", "v_scale"), device_types="cuda")
+def v_quant_with_amax(v: torch.Tensor, v_fp8: torch.Tensor, amax: torch.Tensor, v_scale: torch.Tensor, tensor_layout: int,
+                      scale_max: float) -> None:
+    B, H, S, D = _bhsd(v, tensor_layout)
+    sb, sh, ss = _bhs_strides(v, tensor_layout)
+    with torch.cuda.device(v.device):
+        ws = torch.empty(B * H * D * 4, dtype=torch.uint8, device=v.device)
+        check(lib().sab_v_quant_with_amax(v.data_ptr(), _dt(v), v_fp8.data_ptr(), amax.data_ptr(), v_scale.data_ptr(), B, H, S, D,
+                                          sb, sh, ss, v_fp8.size(-1), float(scale_max), ws.data_ptr(), _stream(v)))
+
+
+@v_quant_with_amax.register_fake
+def _(v, v_fp8, amax, v_scale, tensor_layout, scale_max):
+    return None
+
+
 # ----------------------------------------------------------------------------------------------- attention
 @torch.library.custom_op("sageattention_b200::qk_int8_sv_f8_attn", mutates_args=("output",), device_types="cuda")
 def qk_int8_sv_f8_attn(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, output: torch.Tensor,
                        query_scale: torch.Tensor, key_scale: torch.Tensor, value_scale: Optional[torch.Tensor],
                        value_mean: Optional[torch.Tensor], tensor_layout: int, is_causal: int, q_quant_gran: int,
-                       k_quant_gran: int, sm_scale: float, fold_sm_scale: int, return_lse: int) -> torch.Tensor:
+                       k_quant_gran: int, sm_scale: float, fold_sm_scale: int, return_lse: int,
+                       causal_q_offset: int = 0, kv_seg_len: int = 0) -> torch.Tensor:
     """Same contract as the reference op (sm89_compile.py:48-66): mutates `output`, returns lse
-    ([B,Hq,Sq] fp32 in log2 units, or an empty tensor when return_lse == 0)."""
+    ([B,Hq,Sq] fp32 in log2 units, or an empty tensor when return_lse == 0).
+    kv_seg_len > 0: key/value are the rank-major all-gather of P shards ([P*B,Hkv,kv_seg_len,D] /
+    [P*B,Hkv,D,kv_seg_len]); causal_q_offset is the global index of query row 0."""
     B, Hq, Sq, D = _bhsd(query, tensor_layout)
     _, Hkv, Skv, _ = _bhsd(key, tensor_layout)
+    if kv_seg_len > 0:
+        Skv = (key.size(0) // B) * kv_seg_len
     qs, ks, os_ = _bhs_strides(query, tensor_layout), _bhs_strides(key, tensor_layout), _bhs_strides(output, tensor_layout)
     lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=query.device) if return_lse else \
         torch.empty((0,), dtype=torch.float32, device=query.device)
@@ -156,14 +193,14 @@ def qk_int8_sv_f8_attn(query: torch.Tensor, key: torch.Tensor, value: torch.Tens
                                            lse.data_ptr() if return_lse else None, query_scale.data_ptr(), key_scale.data_ptr(),
                                            _ptr(value_scale), _ptr(value_mean), _dt(output), B, Hq, Hkv, Sq, Skv, D,
                                            *qs, *ks, value.size(-1), *os_, is_causal, q_quant_gran, k_quant_gran,
-                                           float(sm_scale), fold_sm_scale, None, None, None, None, None, 0, None,
-                                           _stream(query)))
+                                           float(sm_scale), fold_sm_scale, None, None, None, None, None, 0,
+                                           causal_q_offset, kv_seg_len, None, _stream(query)))
     return lse
 
 
 @qk_int8_sv_f8_attn.register_fake
 def _(query, key, value, output, query_scale, key_scale, value_scale, value_mean, tensor_layout, is_causal,
-      q_quant_gran, k_quant_gran, sm_scale, fold_sm_scale, return_lse):
+      q_quant_gran, k_quant_gran, sm_scale, fold_sm_scale, return_lse, causal_q_offset=0, kv_seg_len=0):
     B, Hq, Sq, D = _bhsd(query, tensor_layout)
     if return_lse:
         return torch.empty((B, Hq, Sq), dtype=torch.float32, device=query.device)
@@ -187,7 +224,7 @@ def qk_int8_sv_f8_attn_varlen(query: torch.Tensor, key: torch.Tensor, value: tor
                                            value.size(-1), 0, output.stride(1), output.stride(0), is_causal,
                                            _capi.SAB_GRAN_PER_BLOCK, _capi.SAB_GRAN_PER_BLOCK, float(sm_scale), fold_sm_scale,
                                            cu_seqlens_q.data_ptr(), cu_seqlens_k.data_ptr(), cu_pad_v.data_ptr(),
-                                           cu_q_scale.data_ptr(), cu_k_scale.data_ptr(), max_seqlen_q, None, _stream(query)))
+                                           cu_q_scale.data_ptr(), cu_k_scale.data_ptr(), max_seqlen_q, 0, 0, None, _stream(query)))
 
 
 @qk_int8_sv_f8_attn_varlen.register_fake

@@ -1,0 +1,131 @@
+"""Sequence-parallel SageAttention over NCCL (BASELINE.json configs[4]).
+
+One process per GPU.  Rank r holds the r-th contiguous slice of the sequence of Q, K and V
+(``[B,H,S/P,D]`` / ``[B,S/P,H,D]``); the output stays sharded like Q.  The reference library has no
+such code (its example delegates to xfuser, example/parallel_sageattn_cogvideo.py:39-51); the design
+follows from the numerics:
+  * K smoothing must use ONE mean for all keys of a row (softmax is invariant to a common shift of all
+    keys, not to a per-shard shift): fp32 per-channel sums are all-reduced (B*Hkv*D floats).
+  * per-channel V scales need the global |max|: all-reduce(MAX) of B*Hkv*D floats.
+  * what crosses NVLink is the QUANTISED K (int8) and V (fp8) plus the K scales — half the bytes of
+    bf16 K/V.  The all-gather output is consumed in place by the attention kernel (rank-major segment
+    addressing in its TMA coordinates, kv_seg_len), no re-layout pass.
+With S/P a multiple of 128 the per-rank quantisation blocks coincide with the single-GPU blocks, so the
+gathered INT8/FP8 tensors equal the single-GPU ones whenever the all-reduced mean rounds identically.
+"""
+from typing import Any, Optional
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._capi import SAB_GRAN_PER_WARP, SAB_GRAN_PER_THREAD, SAB_SEM_CUDA
+from .core import _check_inputs, _pad_head_dim, _LOG2E
+
+
+# ------------------------------------------------------------------ device-agnostic collective helpers (gloo-testable)
+def global_k_mean(k_sum_local: torch.Tensor, total_len: int, dtype: torch.dtype, group=None) -> torch.Tensor:
+    """[B,H,D] fp32 local per-channel sums -> global mean rounded to `dtype` (k.mean semantics, core.py:773)."""
+    s = k_sum_local.clone()
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    return (s / float(total_len)).to(dtype)
+
+
+def global_abs_max(max_local: torch.Tensor, min_local: torch.Tensor, group=None) -> torch.Tensor:
+    """per-channel max(|max|, |min|) over all ranks (fused.cu:386)."""
+    a = torch.maximum(max_local.abs(), min_local.abs())
+    dist.all_reduce(a, op=dist.ReduceOp.MAX, group=group)
+    return a
+
+
+def gather_rank_major(x: torch.Tensor, group=None) -> torch.Tensor:
+    """all-gather along a new leading rank axis folded into dim 0: [n, ...] -> [P*n, ...]."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * x.size(0),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out.view(torch.uint8) if x.dtype == torch.float8_e4m3fn else out,
+                                x.contiguous().view(torch.uint8) if x.dtype == torch.float8_e4m3fn else x.contiguous(),
+                                group=group)
+    return out
+
+
+def gather_scales(scale_local: torch.Tensor, group=None) -> torch.Tensor:
+    """[B,H,n] per-rank block scales -> [B,H,P*n] in global block order."""
+    world = dist.get_world_size(group)
+    B, H, n = scale_local.shape
+    g = gather_rank_major(scale_local, group).view(world, B, H, n)
+    return g.permute(1, 2, 0, 3).reshape(B, H, world * n).contiguous()
+
+
+# ------------------------------------------------------------------ the SP operator
+def sageattn_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout: str = "HND", is_causal: bool = False,
+                qk_quant_gran: str = "per_thread", sm_scale: Optional[float] = None, pv_accum_dtype: str = "fp32+fp16",
+                smooth_k: bool = True, group=None, **kwargs: Any) -> torch.Tensor:
+    """Sequence-parallel `sageattn_qk_int8_pv_fp8_cuda`: local shards in, local output shard out."""
+    if group is None and not dist.is_initialized():
+        raise RuntimeError("sageattn_sp needs an initialised torch.distributed process group (NCCL)")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dtype = q.dtype
+    _check_inputs(q, k, v)
+    assert qk_quant_gran in ["per_warp", "per_thread"]
+    if pv_accum_dtype not in ("fp32", "fp32+fp32", "fp32+fp16"):
+        raise ValueError(f"Unsupported pv_accum_dtype: {pv_accum_dtype}")
+    lay = 0 if tensor_layout == "NHD" else 1
+    q, k, v, head_dim_og = _pad_head_dim(q, k, v)
+    if sm_scale is None:
+        sm_scale = head_dim_og ** -0.5
+    if lay == 1:
+        B, Hq, Sl, D = q.shape
+        Hk = k.size(1)
+    else:
+        B, Sl, Hq, D = q.shape
+        Hk = k.size(2)
+    assert Sl % 128 == 0, "per-rank sequence length must be a multiple of 128 (quantisation blocks must not straddle ranks)"
+    S = Sl * world
+    dev = q.device
+
+    # 1. global K mean (tiny all-reduce)
+    kmean = None
+    if smooth_k:
+        ksum = torch.empty((B, Hk, D), dtype=torch.float32, device=dev)
+        kmax, kmin = torch.empty_like(ksum), torch.empty_like(ksum)
+        ops.channel_stats(k, ksum, kmax, kmin, lay)
+        kmean = global_k_mean(ksum, S, dtype, group)
+    # 2. global per-channel |V| max (tiny all-reduce)
+    vsum = torch.empty((B, Hk, D), dtype=torch.float32, device=dev)
+    vmax, vmin = torch.empty_like(vsum), torch.empty_like(vsum)
+    ops.channel_stats(v, vsum, vmax, vmin, lay)
+    v_amax = global_abs_max(vmax, vmin, group)
+
+    # 3. quantise the local shards (HND int8 buffers so the all-gather output is [P*B,H,Sl,D])
+    q_int8 = torch.empty((B, Hq, Sl, D), dtype=torch.int8, device=dev)
+    k_int8 = torch.empty((B, Hk, Sl, D), dtype=torch.int8, device=dev)
+    qv = q if lay == 1 else q.transpose(1, 2)
+    kv_ = k if lay == 1 else k.transpose(1, 2)
+    vv = v if lay == 1 else v.transpose(1, 2)
+    if qk_quant_gran == "per_warp":
+        gran = SAB_GRAN_PER_WARP
+        q_scale = torch.empty((B, Hq, Sl // 128 * 4), dtype=torch.float32, device=dev)
+        k_scale = torch.empty((B, Hk, Sl // 64), dtype=torch.float32, device=dev)
+        ops.quant_per_block_int8(qv, None, q_int8, q_scale, 32, 1, SAB_SEM_CUDA, False, 1.0)
+        ops.quant_per_block_int8(kv_, kmean, k_int8, k_scale, 64, 1, SAB_SEM_CUDA, False, 1.0)
+    else:
+        gran = SAB_GRAN_PER_THREAD
+        q_scale = torch.empty((B, Hq, Sl // 128 * 32), dtype=torch.float32, device=dev)
+        k_scale = torch.empty((B, Hk, Sl // 64 * 4), dtype=torch.float32, device=dev)
+        ops.quant_per_thread_int8(qv, None, q_int8, q_scale, 1, False)
+        ops.quant_per_thread_int8(kv_, kmean, k_int8, k_scale, 1, True)
+    scale_max = 2.25 if pv_accum_dtype == "fp32+fp16" else 448.0
+    v_fp8 = torch.empty((B, Hk, D, Sl), dtype=torch.float8_e4m3fn, device=dev)
+    v_scale = torch.empty((B, Hk, D), dtype=torch.float32, device=dev)
+    ops.v_quant_with_amax(vv, v_fp8, v_amax, v_scale, 1, scale_max)
+
+    # 4. all-gather the quantised K / V and the K scales over NVLink
+    k_all = gather_rank_major(k_int8, group)          # [P*B,Hk,Sl,D]
+    v_all = gather_rank_major(v_fp8, group)           # [P*B,Hk,D,Sl]
+    ks_all = gather_scales(k_scale, group)            # [B,Hk,P*n]
+
+    # 5. local attention: this rank's Q rows against all keys
+    o = torch.empty((B, Hq, Sl, D), dtype=dtype, device=dev)
+    ops.qk_int8_sv_f8_attn(q_int8, k_all, v_all, o, q_scale, ks_all, v_scale, None, 1, 1 if is_causal else 0, gran, gran,
+                           sm_scale, 0, 0, rank * Sl, Sl)
+    o = o[..., :head_dim_og]
+    return o if lay == 1 else o.transpose(1, 2)

@@ -1,0 +1,49 @@
+"""world_size-2 gloo tests (CPU) of the sequence-parallel host logic: global K mean, global V |max|, rank-major
+gathers and scale re-ordering must reproduce the single-process quantities."""
+import os, sys
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sageattention_b200 import parallel
+    from oracle import sage_oracle as O
+    torch.manual_seed(0)
+    B, H, S, D = 2, 3, 512, 64
+    k = (torch.randn(B, H, S, D) + 3.0 * torch.randn(B, H, 1, D)).half()
+    v = torch.randn(B, H, S, D).half()
+    Sl = S // world
+    kl, vl = k[:, :, rank * Sl:(rank + 1) * Sl], v[:, :, rank * Sl:(rank + 1) * Sl]
+    # global mean from local fp32 sums == k.mean up to fp16 rounding of an fp32 mean
+    km = parallel.global_k_mean(kl.float().sum(2), S, torch.float16)
+    ref = k.float().mean(2)
+    ok1 = (km.float() - ref).abs().max().item() <= 2 ** -10 * ref.abs().max().item() + 1e-6
+    # global |V| max is exact
+    am = parallel.global_abs_max(vl.float().amax(2), vl.float().amin(2))
+    ok2 = torch.equal(am, v.float().abs().amax(2))
+    # quantise shards with the GLOBAL mean -> gathered tensors equal the single-process quantisation
+    _, _, k8l, ksl = O.quant_per_thread_int8_triton(kl, kl, km.view(B, H, 1, D))
+    _, _, k8, ks = O.quant_per_thread_int8_triton(k, k, km.view(B, H, 1, D))
+    k_all = parallel.gather_rank_major(k8l.contiguous())          # [P*B,H,Sl,D]
+    k_cat = torch.cat([k_all[r * B:(r + 1) * B] for r in range(world)], dim=2)
+    ok3 = torch.equal(k_cat, k8)
+    ok4 = torch.equal(parallel.gather_scales(ksl), ks)
+    ret[rank] = (ok1, ok2, ok3, ok4)
+    dist.destroy_process_group()
+
+
+def test_sp_host_logic_gloo_world2():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert all(ret[r]), f"rank {r}: {ret[r]}"

@@ -132,7 +132,7 @@ def call_attn_debug(q8, k8, v8, qs, ks, vs, gran, causal, sm_scale, dt):
     st = _capi.lib().sab_qk_int8_sv_f8_attn(q8.data_ptr(), k8.data_ptr(), v8.data_ptr(), o.data_ptr(), lse.data_ptr(),
         qs.data_ptr(), ks.data_ptr(), vs.data_ptr(), None, 0 if dt == torch.float16 else 1, B, H, Hk, S, k8.shape[2], D,
         q8.stride(0), q8.stride(1), q8.stride(2), k8.stride(0), k8.stride(1), k8.stride(2), v8.size(-1),
-        o.stride(0), o.stride(1), o.stride(2), causal, gran, gran, sm_scale, 0, None, None, None, None, None, 0,
+        o.stride(0), o.stride(1), o.stride(2), causal, gran, gran, sm_scale, 0, None, None, None, None, None, 0, 0, 0,
         dbg.data_ptr(), torch.cuda.current_stream().cuda_stream)
     _capi.check(st)
     torch.cuda.synchronize()
