@@ -6,7 +6,7 @@ PyTorch fallback (the reference behaves the same way: `from . import _fused`, sa
 import ctypes, os
 from ctypes import c_void_p, c_int, c_int64, c_float, c_char_p
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsageattn_b200.so")
+_LIB_PATH = os.environ.get("SAB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsageattn_b200.so")
 
 SAB_DTYPE_FP16, SAB_DTYPE_BF16 = 0, 1
 SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_WARP, SAB_GRAN_PER_THREAD = 1, 2, 3

@@ -22,6 +22,10 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#ifndef SAB_CVT_MODE
+#define SAB_CVT_MODE 1
+#endif
+
 namespace sab {
 
 constexpr int BM = 128;  // Q rows per CTA
@@ -313,31 +317,44 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         m = m_new;
 
         // ---- P = exp2(S*coef - m_new) -> e4m3 into TMEM (over the S buffer), d += sum(P)
-        // int32 -> fp32 through the 1.5*2^23 magic constant (exact for |S| < 2^22); its bias is folded into the
-        // FMA addend, so the dequant + max-subtract + conversion is ONE FFMA per element.
-        float nb[NG];
+        // int32 -> fp32 through the 1.5*2^23 magic constant (exact for |S| < 2^22: integer add on the ALU pipe +
+        // FADD on the FMA pipe instead of I2F), then the reference's single FFMA fmaf(S, sm_scale', -m)
+        // (attn_utils.cuh:450) -> P is bit-identical to the reference kernel's.
+        const float nm = -m_new;
+        // Packed fp32x2 math (FFMA2 / FADD2): elements (i, i+1) always share a scale group, so the dequant FMA and
+        // the row-sum accumulate issue once per PAIR.  The FMA is IEEE-RN, identical to fmaf per lane.
+        uint64_t coef2[NG];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) nb[g] = fmaf(-12582912.0f, coef[g], -m_new);
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int g = 0; g < NG; ++g) coef2[g] = pack_f2(coef[g], coef[g]);
+        const uint64_t nm2 = pack_f2(nm, nm);
+        uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
         uint32_t pk[BN / 4];
 #pragma unroll
         for (int w = 0; w < BN / 4; ++w) {
           float e[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 4; u += 2) {
             const int i = 4 * w + u;
             const int g = kKT ? ((i & 7) >> 1) : 0;
-            const float f = __uint_as_float(s[i] + 0x4B400000u);
-            e[u] = ex2_approx(fmaf(f, coef[g], nb[g]));
-            if constexpr (MASKED) e[u] = (i < limit) ? e[u] : 0.f;
+            const uint64_t f2 = pack_f2(__int2float_rn(int(s[i])), __int2float_rn(int(s[i + 1])));  // exact (|S| < 2^24)
+            float y0, y1;
+            unpack_f2(ffma2(f2, coef2[g], nm2), y0, y1);   // fmaf(S, sm_scale', -m)  (attn_utils.cuh:450)
+            e[u] = ex2_approx(y0);
+            e[u + 1] = ex2_approx(y1);
+            if constexpr (MASKED) {
+              e[u] = (i < limit) ? e[u] : 0.f;
+              e[u + 1] = (i + 1 < limit) ? e[u + 1] : 0.f;
+            }
+            acc[(w & 1) * 2 + (u >> 1)] = fadd2(acc[(w & 1) * 2 + (u >> 1)], pack_f2(e[u], e[u + 1]));
           }
-          acc0 += e[0];
-          acc1 += e[1];
-          acc2 += e[2];
-          acc3 += e[3];
           pk[w] = pack_e4m3x4(e[0], e[1], e[2], e[3]);
         }
-        d += (acc0 + acc1) + (acc2 + acc3);
+        {
+          float a0, a1, a2, a3;
+          unpack_f2(fadd2(acc[0], acc[1]), a0, a1);
+          unpack_f2(fadd2(acc[2], acc[3]), a2, a3);
+          d += (a0 + a1) + (a2 + a3);
+        }
         tmem_st16(tS, pk);
         // ---- correction: rescale this row of O (in TMEM).  Done AFTER the exponentials so that the wait for PV(j-1)
         //      is hidden behind ~350 instructions of softmax work; PV(j) cannot start before p_full(j) below.
@@ -345,13 +362,19 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_wait_wd(pv_done, (j - 1) & 1);
           tc_fence_after();
           uint32_t r[D / 32][32];
+          const uint64_t alpha2 = pack_f2(alpha, alpha);
 #pragma unroll
           for (int ch = 0; ch < D / 32; ++ch) tmem_ld32(tO + lane_off + ch * 32, r[ch]);
           tc_wait_ld();
 #pragma unroll
           for (int ch = 0; ch < D / 32; ++ch) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[ch][i] = __float_as_uint(__uint_as_float(r[ch][i]) * alpha);
+            for (int i = 0; i < 32; i += 2) {
+              float lo, hi;
+              unpack_f2(fmul2(pack_f2(__uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1])), alpha2), lo, hi);
+              r[ch][i] = __float_as_uint(lo);
+              r[ch][i + 1] = __float_as_uint(hi);
+            }
             tmem_st32(tO + lane_off + ch * 32, r[ch]);
           }
         }

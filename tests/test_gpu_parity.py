@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "tests", "golden")
 TOL_REF = 1e-2      # vs reference kernel / reference fixtures (north star)
-TOL_ORACLE = 5e-3   # vs oracle restated with fp32 PV accumulation
+TOL_ORACLE = 5e-3   # vs oracle restated with fp32 PV accumulation (exact exp2 on CPU vs ex2.approx: rare 1-ulp P flips)
 
 
 @pytest.fixture(scope="module")
