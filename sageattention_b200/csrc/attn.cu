@@ -26,16 +26,23 @@
 #define SAB_CVT_MODE 1
 #endif
 
+#ifdef SAB_TIMELINE
+#define SAB_TL(slot) do { if (tl_on && j >= 16 && j < 48) tl[(j - 16) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define SAB_TL(slot) do {} while (0)
+#endif
+
 namespace sab {
 
 constexpr int BM = 128;  // Q rows per CTA
 constexpr int BN = 64;   // keys per softmax / MMA tile (reference CTA_K)
 constexpr int LK = 128;  // keys per TMA stage (two tiles)
-constexpr int kNumThreads = 256;  // warps 0-3 softmax warpgroup; warps 4-7: TMA, MMA, 2 idle (setmaxnreg is per warpgroup)
+constexpr int kNumThreads = 384;  // warpgroups: 0-3 softmax, 4-7 correction, 8 TMA / 9 MMA / 10-11 idle (setmaxnreg is per warpgroup)
 constexpr uint32_t kTmemCols = 256;
 constexpr float kFp8Offset = 8.807f;      // attn_utils.cuh:30
 constexpr float kMaskValue = -5000000.0f; // attn_utils.cuh:310
 constexpr int kIntSentinel = -(1 << 30);
+constexpr int kAlphaCol = 16;  // column of an S buffer (beyond the 16 P columns) that carries alpha(j) to the correction warps
 
 struct AttnParams {
   const float* q_scale;
@@ -99,29 +106,25 @@ template <int D, bool kKT, typename OutT>
 __global__ void __launch_bounds__(kNumThreads, 2)
 sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  constexpr int NS = (D == 128) ? 2 : 4;      // K/V ring depth (128-key stages)
+  constexpr int NS = (D == 128) ? 3 : 6;      // K/V ring depth (128-key stages)
   constexpr int SWQK = (D == 128) ? 128 : 64; // swizzle span of the Q/K tiles (= row bytes)
   constexpr uint32_t Q_BYTES = BM * D, K_BYTES = LK * D, V_BYTES = D * LK;
   constexpr uint64_t K_HALF = (uint64_t(BN) * D) >> 4;  // descriptor delta: keys 64..127 of a K stage
   constexpr uint64_t V_HALF = uint64_t(BN) >> 4;        // descriptor delta: byte column 64 of a V^T stage
   constexpr int NG = kKT ? 4 : 1;                       // dequant-scale groups per 64-key tile
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;
   uint8_t* sV = sK + NS * K_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * V_BYTES);
   uint64_t* q_full = bars + 0;
-  uint64_t* o_full = bars + 1;
-  uint64_t* pv_done = bars + 2;
-  uint64_t* s_full = bars + 3;   // [2]
-  uint64_t* p_full = bars + 5;   // [2]
-  uint64_t* k_full = bars + 7;
-  uint64_t* k_empty = k_full + NS;
-  uint64_t* v_full = k_empty + NS;
-  uint64_t* v_empty = v_full + NS;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(v_empty + NS);
+  uint64_t* s_full = bars + 1;    // [2] step(t) retired: S(t+2) ready in buffer t&1 AND PV(t) accumulated into O
+  uint64_t* p_full = bars + 3;    // [2] 256 arrivals: P(j) stored (softmax) + O rescaled (correction)
+  uint64_t* a_full = bars + 5;    // [2] 128 arrivals: alpha(j) published by the softmax warps
+  uint64_t* kv_full = bars + 7;   // [NS] TMA bytes landed (K + V^T of a 128-key stage)
+  uint64_t* kv_empty = kv_full + NS;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(kv_empty + NS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,100 +154,139 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int n_st = (n_kv + 1) / 2;                   // 128-key TMA stages
 
   // ---------------- one-time setup
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();     // swizzled tiles need a 1 KB-aligned base
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    mbar_init(o_full, 1);
-    mbar_init(pv_done, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(s_full + i, 1);
-      mbar_init(p_full + i, 128);
+      mbar_init(p_full + i, 256);
+      mbar_init(a_full + i, 128);
     }
     for (int i = 0; i < NS; ++i) {
-      mbar_init(k_full + i, 1);
-      mbar_init(k_empty + i, 1);
-      mbar_init(v_full + i, 1);
-      mbar_init(v_empty + i, 1);
+      mbar_init(kv_full + i, 1);
+      mbar_init(kv_empty + i, 1);
     }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<kTmemCols>(tmem_holder);
+  if (warp == 9) tmem_alloc<kTmemCols>(tmem_holder);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t tO = tmem_base + 128;  // cols [128,128+D); S buffer b at cols [64b, 64b+64), P(b) at its first 16
+  // parity of the phase of s_full[t & 1] that completes when step(t-2) retires (S(t) ready / PV(t-2) accumulated)
+  auto s_parity = [](int t) { return uint32_t(t >> 1) & 1u; };
 
-  if (warp >= 4) {
+  if (warp >= 8) {
     setmaxnreg_dec_48();
-    if (warp == 4) {
-    // =============================== TMA producer ===============================
-    if (lane == 0 && n_kv > 0) {
-      mbar_expect_tx(q_full, Q_BYTES);
-      tma_load_4d(sQ, &tmQ, q_full, 0, q_off + qt * BM, h, tb);
-      for (int jj = 0; jj < n_st; ++jj) {
-        const int s = jj % NS;
-        const uint32_t ph = (jj / NS) & 1;
-        int kc = k_off + jj * LK, vc = v_off + jj * LK, kb = tb;
-        if (p.kv_seg_len > 0) {  // all-gathered layout: segment-major
-          const int seg = (jj * LK) / p.kv_seg_len;
-          kc = vc = jj * LK - seg * p.kv_seg_len;
-          kb = seg * p.B + b;
+    if (warp == 8) {
+      // =============================== TMA producer ===============================
+      if (lane == 0 && n_kv > 0) {
+        mbar_expect_tx(q_full, Q_BYTES);
+        tma_load_4d(sQ, &tmQ, q_full, 0, q_off + qt * BM, h, tb);
+        for (int jj = 0; jj < n_st; ++jj) {
+          const int s = jj % NS;
+          const uint32_t ph = (jj / NS) & 1;
+          int kc = k_off + jj * LK, vc = v_off + jj * LK, kb = tb;
+          if (p.kv_seg_len > 0) {  // all-gathered layout: segment-major
+            const int seg = (jj * LK) / p.kv_seg_len;
+            kc = vc = jj * LK - seg * p.kv_seg_len;
+            kb = seg * p.B + b;
+          }
+          mbar_wait_wd(kv_empty + s, ph ^ 1);
+          mbar_expect_tx(kv_full + s, K_BYTES + V_BYTES);
+          tma_load_4d(sK + s * K_BYTES, &tmK, kv_full + s, 0, kc, hk, kb);
+          tma_load_4d(sV + s * V_BYTES, &tmV, kv_full + s, vc, 0, hk, kb);
         }
-        mbar_wait_wd(k_empty + s, ph ^ 1);
-        mbar_expect_tx(k_full + s, K_BYTES);
-        tma_load_4d(sK + s * K_BYTES, &tmK, k_full + s, 0, kc, hk, kb);
-        mbar_wait_wd(v_empty + s, ph ^ 1);
-        mbar_expect_tx(v_full + s, V_BYTES);
-        tma_load_4d(sV + s * V_BYTES, &tmV, v_full + s, vc, 0, hk, kb);
       }
-    }
-    } else if (warp == 5) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0 && n_kv > 0) {
-      constexpr uint32_t idesc_qk = make_idesc(2, 1, 1, BM, BN);  // s32 <- s8 x s8, 128 x 64
-      constexpr uint32_t idesc_pv = make_idesc(1, 0, 0, BM, D);   // f32 <- e4m3 x e4m3, 128 x D
-      const uint64_t dQ = make_smem_desc<SWQK>(smem_u32(sQ));
-      auto issue_qk = [&](int j) {
-        const int jj = j >> 1, s = jj % NS, half = j & 1;
-        if (half == 0) {
-          mbar_wait_wd(k_full + s, (jj / NS) & 1);
-          tc_fence_after();
-        }
-        const uint64_t dK = make_smem_desc<SWQK>(smem_u32(sK + s * K_BYTES)) + half * K_HALF;
-        const uint32_t tS = tmem_base + (j & 1) * BN;
+    } else if (warp == 9) {
+      // =============================== MMA issuer ===============================
+      // step(t) = PV(t) ; QK(t+2) ; commit -> s_full[t&1].   In-order tensor pipe:  QK0 QK1 | PV0 QK2 | PV1 QK3 | ...
+      if (lane == 0 && n_kv > 0) {
+        constexpr uint32_t idesc_qk = make_idesc(2, 1, 1, BM, BN);  // s32 <- s8 x s8, 128 x 64
+        constexpr uint32_t idesc_pv = make_idesc(1, 0, 0, BM, D);   // f32 <- e4m3 x e4m3, 128 x D
+        const uint64_t dQ = make_smem_desc<SWQK>(smem_u32(sQ));
+        const uint64_t dK0 = make_smem_desc<SWQK>(smem_u32(sK));
+        const uint64_t dV0 = make_smem_desc<128>(smem_u32(sV));
+        auto issue_qk = [&](int t) {
+          const int st = (t >> 1) % NS;
+          const uint64_t dK = dK0 + uint64_t(st) * (K_BYTES >> 4) + uint64_t(t & 1) * K_HALF;
+          const uint32_t tS = tmem_base + (t & 1) * BN;
 #pragma unroll
-        for (int k = 0; k < D / 32; ++k) umma_i8_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_qk, k > 0);
-        if (half == 1 || j == n_kv - 1) tc_commit(k_empty + s);  // K stage reusable once its MMAs retire
-        tc_commit(s_full + (j & 1));
-      };
-      mbar_wait_wd(q_full, 0);
-      issue_qk(0);
-      if (n_kv > 1) issue_qk(1);
-      for (int j = 0; j < n_kv; ++j) {
-        const int jj = j >> 1, s = jj % NS, half = j & 1;
-        mbar_wait_wd(p_full + (j & 1), (j >> 1) & 1);   // P(j) stored by all 128 rows (also: S(j) fully consumed)
+          for (int k = 0; k < D / 32; ++k) umma_i8_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_qk, k > 0);
+        };
+        mbar_wait_wd(q_full, 0);
+        mbar_wait_wd(kv_full + 0, 0);
         tc_fence_after();
-        if (half == 0) {
-          mbar_wait_wd(v_full + s, (jj / NS) & 1);
-          tc_fence_after();
+        issue_qk(0);
+        tc_commit(s_full + 0);
+        if (n_kv > 1) {
+          issue_qk(1);
+          tc_commit(s_full + 1);
         }
-        const uint64_t dV = make_smem_desc<128>(smem_u32(sV + s * V_BYTES)) + half * V_HALF;
-        const uint32_t tP = tmem_base + (j & 1) * BN;
+#ifdef SAB_TIMELINE
+        const bool tl_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+        long long* tl = reinterpret_cast<long long*>(p.dbg) + 4096;
+#endif
+        for (int j = 0; j < n_kv; ++j) {
+          SAB_TL(8);
+          // operands of this step that come from a NEW stage: wait for them while P(j) is still being produced
+          if ((j & 1) == 0 && j + 2 < n_kv) mbar_wait_wd(kv_full + ((j + 2) >> 1) % NS, (((j + 2) >> 1) / NS) & 1);
+          mbar_wait_wd(p_full + (j & 1), (j >> 1) & 1);   // P(j) stored + O rescaled (also: S(j) fully consumed)
+          tc_fence_after();
+          SAB_TL(9);
+          const int st = (j >> 1) % NS;
+          const uint64_t dV = dV0 + uint64_t(st) * (V_BYTES >> 4) + uint64_t(j & 1) * V_HALF;
+          const uint32_t tP = tmem_base + (j & 1) * BN;
 #pragma unroll
-        for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tO, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
-        if (half == 1 || j == n_kv - 1) tc_commit(v_empty + s);
-        tc_commit(pv_done);                              // phase j: O holds tiles 0..j
-        if (j + 2 < n_kv) issue_qk(j + 2);               // reuses S buffer j&1 (after PV(j): in-order pipe)
+          for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tO, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
+          SAB_TL(10);
+          if (j + 2 < n_kv) issue_qk(j + 2);               // reuses S buffer j&1 (after PV(j): in-order pipe)
+          tc_commit(s_full + (j & 1));
+          if ((j & 1) == 1 || j == n_kv - 1) tc_commit(kv_empty + st);   // stage fully consumed once this step retires
+          SAB_TL(11);
+        }
       }
-      tc_commit(o_full);
     }
+  } else if (warp >= 4) {
+    // =============================== correction: rescale O when the running max moved ===============================
+    // stays at the launch allocation (80 regs): 128 x (112 + 80 + 48) = 30720 = the CTA's register pool
+    const int row = (warp - 4) * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>((warp - 4) * 32) << 16;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait_wd(a_full + (j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      const float alpha = __uint_as_float(tmem_ld1(tmem_base + lane_off + (j & 1) * BN + kAlphaCol));
+      tc_wait_ld();
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        mbar_wait_wd(s_full + ((j + 1) & 1), s_parity(j + 1));   // step(j-1) retired: PV(j-1) is in O
+        tc_fence_after();
+        const uint64_t alpha2 = pack_f2(alpha, alpha);
+#pragma unroll
+        for (int ch = 0; ch < D / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(tO + lane_off + ch * 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float lo, hi;
+            unpack_f2(fmul2(pack_f2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), alpha2), lo, hi);
+            r[i] = __float_as_uint(lo);
+            r[i + 1] = __float_as_uint(hi);
+          }
+          tmem_st32(tO + lane_off + ch * 32, r);
+        }
+        tc_wait_st();
+      }
+      tc_fence_before();
+      mbar_arrive(p_full + (j & 1));
     }
   } else {
-    setmaxnreg_inc_208();
-    // =============================== softmax / correction / epilogue ===============================
+    setmaxnreg_inc_112();
+    // =============================== softmax / epilogue ===============================
     const int row = warp * 32 + lane;  // TMEM lane == Q row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     const int q_row = qt * BM + row;  // row index inside the sequence
@@ -260,6 +302,10 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
     float m = kMaskValue;  // running max (log2 units, includes the -8.807 offset)
     float d = 0.f;         // running sum of fp32 P
+#ifdef SAB_TIMELINE
+    const bool tl_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+    long long* tl = reinterpret_cast<long long*>(p.dbg) + 4096;
+#endif
 
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t tS = tmem_base + lane_off + (j & 1) * BN;
@@ -272,8 +318,10 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (p.causal) limit = min(limit, p.causal_q_offset + q_row - j * BN + 1);
       const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && (j + 1) * BN > p.causal_q_offset + qt * BM + 1);
 
-      mbar_wait_wd(s_full + (j & 1), (j >> 1) & 1);
+      SAB_TL(0);
+      mbar_wait_wd(s_full + (j & 1), s_parity(j));
       tc_fence_after();
+      SAB_TL(1);
       uint32_t s[BN];
       {
         uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
@@ -282,6 +330,7 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld32(tS + 32, hi);
         tc_wait_ld();
       }
+      SAB_TL(2);
       if (dump && j == 0) {
 #pragma unroll
         for (int i = 0; i < BN; ++i) p.dbg[row * BN + i] = int(s[i]);
@@ -304,8 +353,15 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
             for (int i8 = 0; i8 < BN; i8 += 8) v = __vimax3_s32(v, int(s[i8 + 2 * g]), int(s[i8 + 2 * g + 1]));
           } else {
+            int v0 = kIntSentinel, v1 = kIntSentinel, v2 = kIntSentinel, v3 = kIntSentinel;   // 4 chains: ILP
 #pragma unroll
-            for (int i = 0; i < BN; i += 2) v = __vimax3_s32(v, int(s[i]), int(s[i + 1]));
+            for (int i = 0; i < BN; i += 8) {
+              v0 = __vimax3_s32(v0, int(s[i]), int(s[i + 1]));
+              v1 = __vimax3_s32(v1, int(s[i + 2]), int(s[i + 3]));
+              v2 = __vimax3_s32(v2, int(s[i + 4]), int(s[i + 5]));
+              v3 = __vimax3_s32(v3, int(s[i + 6]), int(s[i + 7]));
+            }
+            v = max(max(v0, v1), max(v2, v3));
           }
           float c = float(v) * coef[g];
           if constexpr (MASKED) c = (v == kIntSentinel) ? kMaskValue : c;
@@ -315,14 +371,19 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float alpha = ex2_approx(m - m_new);
         d *= alpha;
         m = m_new;
-
-        // ---- P = exp2(S*coef - m_new) -> e4m3 into TMEM (over the S buffer), d += sum(P)
-        // int32 -> fp32 through the 1.5*2^23 magic constant (exact for |S| < 2^22: integer add on the ALU pipe +
-        // FADD on the FMA pipe instead of I2F), then the reference's single FFMA fmaf(S, sm_scale', -m)
-        // (attn_utils.cuh:450) -> P is bit-identical to the reference kernel's.
+        // publish alpha through a dead column of this S buffer (shared memory is full: two CTAs per SM): the correction
+        // warpgroup rescales this row of O (in TMEM) concurrently with the exponentials below
+        tmem_st1(tS + kAlphaCol, __float_as_uint(alpha));
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(a_full + (j & 1));
         const float nm = -m_new;
-        // Packed fp32x2 math (FFMA2 / FADD2): elements (i, i+1) always share a scale group, so the dequant FMA and
-        // the row-sum accumulate issue once per PAIR.  The FMA is IEEE-RN, identical to fmaf per lane.
+        SAB_TL(3);
+
+        // ---- P = exp2(S*coef - m_new) -> e4m3 into TMEM (over the S buffer), d += sum(P).
+        // I2FP is exact (|S| < 2^24) and the FMA is the reference's fmaf(S, sm_scale', -m) (attn_utils.cuh:450), so P
+        // is bit-identical to the reference kernel's.  Packed fp32x2 math (FFMA2 / FADD2): elements (i, i+1) always
+        // share a scale group, so the dequant FMA and the row-sum accumulate issue once per PAIR.
         uint64_t coef2[NG];
 #pragma unroll
         for (int g = 0; g < NG; ++g) coef2[g] = pack_f2(coef[g], coef[g]);
@@ -336,11 +397,15 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int u = 0; u < 4; u += 2) {
             const int i = 4 * w + u;
             const int g = kKT ? ((i & 7) >> 1) : 0;
-            const uint64_t f2 = pack_f2(__int2float_rn(int(s[i])), __int2float_rn(int(s[i + 1])));  // exact (|S| < 2^24)
+            const uint64_t f2 = pack_f2(__int2float_rn(int(s[i])), __int2float_rn(int(s[i + 1])));
             float y0, y1;
-            unpack_f2(ffma2(f2, coef2[g], nm2), y0, y1);   // fmaf(S, sm_scale', -m)  (attn_utils.cuh:450)
+            unpack_f2(ffma2(f2, coef2[g], nm2), y0, y1);
+#ifdef SAB_EXP_NO_MUFU
+            e[u] = y0 * 0.001f; e[u + 1] = y1 * 0.001f;
+#else
             e[u] = ex2_approx(y0);
             e[u + 1] = ex2_approx(y1);
+#endif
             if constexpr (MASKED) {
               e[u] = (i < limit) ? e[u] : 0.f;
               e[u + 1] = (i + 1 < limit) ? e[u + 1] : 0.f;
@@ -355,29 +420,8 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           unpack_f2(fadd2(acc[2], acc[3]), a2, a3);
           d += (a0 + a1) + (a2 + a3);
         }
+        SAB_TL(4);
         tmem_st16(tS, pk);
-        // ---- correction: rescale this row of O (in TMEM).  Done AFTER the exponentials so that the wait for PV(j-1)
-        //      is hidden behind ~350 instructions of softmax work; PV(j) cannot start before p_full(j) below.
-        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-          mbar_wait_wd(pv_done, (j - 1) & 1);
-          tc_fence_after();
-          uint32_t r[D / 32][32];
-          const uint64_t alpha2 = pack_f2(alpha, alpha);
-#pragma unroll
-          for (int ch = 0; ch < D / 32; ++ch) tmem_ld32(tO + lane_off + ch * 32, r[ch]);
-          tc_wait_ld();
-#pragma unroll
-          for (int ch = 0; ch < D / 32; ++ch) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float lo, hi;
-              unpack_f2(fmul2(pack_f2(__uint_as_float(r[ch][i]), __uint_as_float(r[ch][i + 1])), alpha2), lo, hi);
-              r[ch][i] = __float_as_uint(lo);
-              r[ch][i + 1] = __float_as_uint(hi);
-            }
-            tmem_st32(tO + lane_off + ch * 32, r[ch]);
-          }
-        }
         if (dump && j == 0) {
 #pragma unroll
           for (int w = 0; w < BN / 4; ++w) p.dbg[128 * BN + row * 16 + w] = int(pk[w]);
@@ -386,9 +430,12 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (masked_tile) tile(std::true_type{});
       else tile(std::false_type{});
 
+      SAB_TL(5);
       tc_wait_st();
+      SAB_TL(6);
       tc_fence_before();
       mbar_arrive(p_full + (j & 1));
+      SAB_TL(7);
     }
 
     // ---- epilogue: O / d * v_scale (+ v_mean) -> fp16/bf16, 16-byte stores (…sm89.cuh:572-703)
@@ -398,7 +445,7 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float* vs = p.v_scale ? p.v_scale + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D : nullptr;
     const float* vm = p.v_mean ? p.v_mean + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D : nullptr;
     if (n_kv > 0) {
-      mbar_wait_wd(o_full, 0);
+      mbar_wait_wd(s_full + ((n_kv + 1) & 1), s_parity(n_kv + 1));   // step(n_kv-1) retired: O is final
       tc_fence_after();
       const float inv = rcp_approx(d);
 #pragma unroll
@@ -449,7 +496,7 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   // ---------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == 9) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -493,9 +540,9 @@ static int make_map_u8(CUtensorMap* map, const void* base, uint64_t d0, uint64_t
 template <int D, bool kKT, typename OutT>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  constexpr int NS = (D == 128) ? 2 : 4;
-  // 1 KB alignment slack + tiles + barriers; at least 80 KB so that exactly two CTAs (2 x 256 TMEM columns) fit an SM
-  size_t smem = 1024 + size_t(BM) * D + size_t(NS) * 2 * LK * D + 256;
+  constexpr int NS = (D == 128) ? 3 : 6;
+  // Q tile + NS x (K + V^T stage) + barriers = 112.1 KB -> exactly two CTAs (2 x 256 TMEM columns) fit the 228 KB of an SM
+  size_t smem = size_t(BM) * D + size_t(NS) * 2 * LK * D + 256;
   if (smem < 80 * 1024) smem = 80 * 1024;
   auto kern = sage_attn_fwd_kernel<D, kKT, OutT>;
   static bool configured = false;

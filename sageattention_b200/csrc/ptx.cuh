@@ -52,7 +52,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
       ::"r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
       : "memory");
 }
-__device__ __forceinline__ void setmaxnreg_inc_208() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;"); }
+// launch_bounds(384, 2) -> 80 registers per thread at launch = a 30720-register pool per CTA, re-split 112 / 80 / 48
+__device__ __forceinline__ void setmaxnreg_inc_112() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;"); }
 __device__ __forceinline__ void setmaxnreg_dec_48() { asm volatile("setmaxnreg.dec.sync.aligned.u32 48;"); }
 
 // ------------------------------------------------------------------ TMA
@@ -139,6 +140,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" ::SAB_W4(r, 0),
                SAB_W4(r, 4), "r"(taddr)
                : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%1], {%0};" ::"r"(v), "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
 }
 #undef SAB_R4
 #undef SAB_W4
