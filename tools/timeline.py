@@ -30,4 +30,5 @@ for j in range(0, 20):
     d = [int(r[i + 1] - r[i]) for i in range(7)]
     nxt = int(tl[j + 1, 0] - r[0]) if j + 1 < 32 else -1
     m = [int(r[9] - r[8]), int(r[10] - r[9]), int(r[11] - r[10])]
-    print(f"tile {16 + j}: start {int(r[0] - t0):7d} | wait_s {d[0]:5d} ldS {d[1]:5d} max {d[2]:5d} exp {d[3]:5d} st+resc {d[4]:5d} waitst {d[5]:5d} arrive {d[6]:5d} | iter {nxt:6d} || mma wait_p {m[0]:6d} pv {m[1]:5d} qk {m[2]:5d}  P_ok-arrive {int(r[9] - r[7]):6d}  S_ok(next)-QKissued {int(tl[j + 1, 1] - 0):d}")
+    st = [int(r[13] - r[12]), int(r[14] - r[13]), int(r[15] - r[14])]
+    print(f"tile {16 + j}: start {int(r[0] - t0):7d} | wait_m {d[0]:5d} ldS {d[1]:5d} alpha {d[2]:5d} exp {d[3]:5d} st {d[4]:5d} waitst {d[5]:5d} arrive {d[6]:5d} | iter {nxt:6d} || mma wait_p {m[0]:6d} pv {m[1]:5d} qk {m[2]:5d} P_ok-arrive {int(r[9] - r[7]):6d} || stats wait_s {st[0]:5d} max+pub {st[1]:5d} resc+arrive {st[2]:5d} m_pub-exp_top {int(r[14] - r[0]):6d}")
