@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(256) quant_int8_kernel(const QuantParams p) {
 
   __shared__ float s_row_amax[128];
   __shared__ float s_scale[32];
+  __shared__ float s_inv[32];   // RN(1/scale): fast path of the Triton-semantics division
 
   float v[NP][8];
 #pragma unroll
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(256) quant_int8_kernel(const QuantParams p) {
       mult = scale;
     }
     s_scale[g] = mult;
+    s_inv[g] = __fdiv_rn(1.0f, mult);
     const int gcol = tile * ngroups + g;
     if (varlen) {
       const int nblk = (S + p.blk - 1) / p.blk;
@@ -250,11 +252,20 @@ __global__ void __launch_bounds__(256) quant_int8_kernel(const QuantParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) q[i] = cvt_rni_sat_s8(v[ps][i] * mult);
     } else {
+      // x / scale must be the correctly-rounded IEEE quotient to stay bit-exact with the reference (Triton `x / scale`).
+      // Fast path: x * RN(1/scale) differs from it by < 2.4e-5 at |y| <= 127.5, so after adding the +-0.5 rounding
+      // offset the truncation can only differ when z lies within 1e-4 of an integer; only those (rare, ~2e-4)
+      // elements take the exact division.  Removes the per-element MUFU.RCP + Newton sequence (4x kernel time).
+      const float inv = s_inv[g];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float y = __fdiv_rn(v[ps][i], mult);
-        y = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);   // quant_per_block.py:43-45
-        q[i] = static_cast<int8_t>(static_cast<int>(y));  // truncation toward zero
+        float y = v[ps][i] * inv;
+        float z = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);     // quant_per_block.py:43-45
+        if (fabsf(z - rintf(z)) < 1e-4f) {
+          y = __fdiv_rn(v[ps][i], mult);
+          z = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
+        }
+        q[i] = static_cast<int8_t>(static_cast<int>(z));     // truncation toward zero
       }
     }
     *reinterpret_cast<uint2*>(ob + int64_t(row) * p.oss) = *reinterpret_cast<uint2*>(q);

@@ -109,6 +109,29 @@ def test_quant_vs_oracle(env, shape):
         assert torch.allclose(vs.cpu(), es, rtol=3e-7, atol=0)
 
 
+def test_quant_per_thread_bit_exact_at_full_size(env):
+    """BASELINE-size tensor (4x32x8192x128): the fast-path/exact-division split of the Triton-semantics quantiser must be
+    bit-identical to the plain IEEE formula (quant_per_thread.py:41-44), restated here with torch ops on the GPU."""
+    sab, ops, O = env
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, H, S, D = 4, 32, 8192, 128
+    q = torch.randn(B, H, S, D, device="cuda", generator=g).bfloat16()
+    k = (torch.randn(B, H, S, D, device="cuda", generator=g) + 2.0).bfloat16()
+    km = k.mean(dim=2, keepdim=True)
+    q8, qs, k8, ks = sab.per_thread_int8(q, k, km)
+    xf = q.float().view(B, H, S // 32, 4, 8, D)
+    c127 = torch.tensor(127.0, device="cuda")   # tensor divisor: torch turns division by a python scalar into a multiply
+    sc = xf.abs().amax(dim=(3, 5)) / c127 + 0.0000001
+    y = xf / sc[:, :, :, None, :, None]
+    e8 = torch.trunc(y + 0.5 * torch.where(y >= 0, 1.0, -1.0)).to(torch.int8).view(B, H, S, D)
+    assert torch.equal(qs, sc.reshape(B, H, -1)) and torch.equal(q8, e8)
+    kf = (k - km).float().view(B, H, S // 64, 8, 4, 2, D)
+    sc = kf.abs().amax(dim=(3, 5, 6)) / c127 + 0.0000001
+    y = kf / sc[:, :, :, None, :, None, None]
+    e8 = torch.trunc(y + 0.5 * torch.where(y >= 0, 1.0, -1.0)).to(torch.int8).view(B, H, S, D)
+    assert torch.equal(ks, sc.reshape(B, H, -1)) and torch.equal(k8, e8)
+
+
 def test_quant_bit_exact_vs_real_reference_kernels(env):
     sab, ops, O = env
     rf = _ref("ref_fused")
@@ -170,7 +193,9 @@ def test_attention_vs_oracle(env, c):
     eps = 2.0 ** -10 if q.dtype == torch.float16 else 2.0 ** -7
     ulp = torch.exp2(torch.floor(torch.log2(oe.float().abs().clamp_min(2.0 ** -14)))) * eps
     assert (err > 1.01 * ulp + 2e-4).float().mean().item() < 2e-2   # a flipped P touches every column of its row
-    assert (lse.cpu() - le).abs().max().item() <= 2e-3
+    # lse = kernel lse (agrees to 1e-4 with the reference kernel, test below) + q.km correction computed by torch.matmul in
+    # the INPUT dtype (core.py:782-786): cuBLAS vs CPU rounding of that fp16/bf16 product dominates
+    assert (lse.cpu() - le).abs().max().item() <= (1e-2 if q.dtype == torch.float16 else 6e-2)
     # NHD layout: same numbers through the other stride set
     qn, kn, vn = (t.transpose(1, 2).contiguous() for t in (q, k, v))
     on = sab.sageattn_qk_int8_pv_fp8_cuda(qn, kn, vn, tensor_layout="NHD", is_causal=c["causal"], qk_quant_gran=c["gran"], pv_accum_dtype=c["acc"])
