@@ -16,90 +16,12 @@
 // un-rounded fp32 P, top-left causal alignment, rcp/lg2/ex2 .approx).  The one deliberate difference: PV accumulates
 // in fp32 inside the tensor core across tiles (the reference's f16 first-level accumulator is a consumer-GPU speed
 // trick; tcgen05 f32 accumulation is full rate).
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <type_traits>
-#include "common.cuh"
-#include "ptx.cuh"
-
-#ifndef SAB_CVT_MODE
-#define SAB_CVT_MODE 1
-#endif
-
-#ifdef SAB_TIMELINE
-#define SAB_TL(slot) do { if (tl_on && j >= 16 && j < 48) tl[(j - 16) * 16 + (slot)] = clock64(); } while (0)
-#else
-#define SAB_TL(slot) do {} while (0)
-#endif
+#include <cstdlib>
+#include "attn_common.cuh"
 
 namespace sab {
 
-constexpr int BM = 128;  // Q rows per CTA
-constexpr int BN = 64;   // keys per softmax / MMA tile (reference CTA_K)
-constexpr int LK = 128;  // keys per TMA stage (two tiles)
 constexpr int kNumThreads = 384;  // warpgroups: 0-3 softmax, 4-7 correction, 8 TMA / 9 MMA / 10-11 idle (setmaxnreg is per warpgroup)
-constexpr uint32_t kTmemCols = 256;
-constexpr float kFp8Offset = 8.807f;      // attn_utils.cuh:30
-constexpr float kMaskValue = -5000000.0f; // attn_utils.cuh:310
-constexpr int kIntSentinel = -(1 << 30);
-constexpr int kAlphaCol = 16;  // column of an S buffer (beyond the 16 P columns) that carries alpha(j) to the correction warps
-
-struct AttnParams {
-  const float* q_scale;
-  const float* k_scale;
-  const float* v_scale;  // nullable
-  const float* v_mean;   // nullable
-  void* out;
-  float* lse;  // nullable
-  int64_t o_stride_b, o_stride_h, o_stride_s;
-  int B, Hq, Hkv, Sq, Sk;
-  int n_q_tiles;
-  int causal;
-  float sm_scale_log2;
-  int q_mult;            // scales per 128-row Q block: 1 / 4 / 32
-  int q_gran;            // 1 / 2 / 3
-  int k_mult;            // scales per 64-key block: 1 / 4
-  int64_t qs_stride_bh;  // dense: scales per (b,h); varlen: unused
-  int64_t ks_stride_bh;
-  int qs_stride_idx;     // dense 1, varlen Hq
-  int ks_stride_idx;     // dense 1, varlen Hkv
-  const int32_t* cu_q;   // varlen (nullable)
-  const int32_t* cu_k;
-  const int32_t* cu_v;
-  const int32_t* cu_qs;
-  const int32_t* cu_ks;
-  int causal_q_offset;   // global index of query row 0 (sequence-parallel causal)
-  int kv_seg_len;        // > 0: K/V are rank-major all-gathered segments of this many keys
-  int32_t* dbg;          // nullable debug dump (CTA 0 only)
-};
-
-__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
-#ifdef SAB_WATCHDOG
-  // Debug build: bounded spin, a protocol bug traps (visible as a launch failure) instead of hanging the GPU.
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("sab: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-#else
-  mbar_wait(bar, parity);
-#endif
-}
-
-template <typename T>
-__device__ __forceinline__ uint32_t pack2(float a, float b);
-template <>
-__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-template <>
-__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 // D: head dim (64 / 128).  kKT: per-thread K scales (4 per 64-key block) instead of 1.  OutT: __half / bf16.
 template <int D, bool kKT, typename OutT>
@@ -205,30 +127,33 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     } else if (warp == 9) {
       // =============================== MMA issuer ===============================
       // step(t) = PV(t) ; QK(t+2) ; commit -> s_full[t&1].   In-order tensor pipe:  QK0 QK1 | PV0 QK2 | PV1 QK3 | ...
-      if (lane == 0 && n_kv > 0) {
+      if (n_kv > 0) {   // whole warp runs the loop (uniform control flow); one elected lane issues
         constexpr uint32_t idesc_qk = make_idesc(2, 1, 1, BM, BN);  // s32 <- s8 x s8, 128 x 64
         constexpr uint32_t idesc_pv = make_idesc(1, 0, 0, BM, D);   // f32 <- e4m3 x e4m3, 128 x D
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint64_t dQ = make_smem_desc<SWQK>(smem_u32(sQ));
         const uint64_t dK0 = make_smem_desc<SWQK>(smem_u32(sK));
         const uint64_t dV0 = make_smem_desc<128>(smem_u32(sV));
         auto issue_qk = [&](int t) {
           const int st = (t >> 1) % NS;
           const uint64_t dK = dK0 + uint64_t(st) * (K_BYTES >> 4) + uint64_t(t & 1) * K_HALF;
-          const uint32_t tS = tmem_base + (t & 1) * BN;
+          const uint32_t tS = tmem_u + (t & 1) * BN;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < D / 32; ++k) umma_i8_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_qk, k > 0);
+            for (int k = 0; k < D / 32; ++k) umma_i8_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_qk, k > 0);
+          }
         };
         mbar_wait_wd(q_full, 0);
         mbar_wait_wd(kv_full + 0, 0);
         tc_fence_after();
         issue_qk(0);
-        tc_commit(s_full + 0);
+        if (elect_one()) tc_commit(s_full + 0);
         if (n_kv > 1) {
           issue_qk(1);
-          tc_commit(s_full + 1);
+          if (elect_one()) tc_commit(s_full + 1);
         }
 #ifdef SAB_TIMELINE
-        const bool tl_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+        const bool tl_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
         long long* tl = reinterpret_cast<long long*>(p.dbg) + 4096;
 #endif
         for (int j = 0; j < n_kv; ++j) {
@@ -240,13 +165,17 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           SAB_TL(9);
           const int st = (j >> 1) % NS;
           const uint64_t dV = dV0 + uint64_t(st) * (V_BYTES >> 4) + uint64_t(j & 1) * V_HALF;
-          const uint32_t tP = tmem_base + (j & 1) * BN;
+          const uint32_t tP = tmem_u + (j & 1) * BN;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tO, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
+            for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tmem_u + 128, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
+          }
           SAB_TL(10);
           if (j + 2 < n_kv) issue_qk(j + 2);               // reuses S buffer j&1 (after PV(j): in-order pipe)
-          tc_commit(s_full + (j & 1));
-          if ((j & 1) == 1 || j == n_kv - 1) tc_commit(kv_empty + st);   // stage fully consumed once this step retires
+          if (elect_one()) {
+            tc_commit(s_full + (j & 1));
+            if ((j & 1) == 1 || j == n_kv - 1) tc_commit(kv_empty + st);   // stage fully consumed once this step retires
+          }
           SAB_TL(11);
         }
       }
@@ -537,9 +466,30 @@ static int make_map_u8(CUtensorMap* map, const void* base, uint64_t d0, uint64_t
   return SAB_OK;
 }
 
+// attn_pair.cu
+template <int D, bool kKT, typename OutT>
+int launch_attn_pair(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                     cudaStream_t stream);
+
+// SAB_ATTN_KERNEL=single|pair selects the kernel.  Default: single (one Q tile per CTA, two CTAs per SM) — measured
+// faster on B200 (1.28 vs 1.06 PFLOP/s at hd128 S=8192); pair (attn_pair.cu: two Q tiles per CTA, exp ping-pong) is kept
+// as an experiment: with one warp per scheduler in the exp phase it is latency-bound.
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAB_ATTN_KERNEL");
+    v = (e != nullptr && e[0] == 'p') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int D, bool kKT, typename OutT>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
+  if (use_pair_kernel()) {
+    dim3 g2((grid.x + 1) / 2, grid.y, grid.z);
+    return launch_attn_pair<D, kKT, OutT>(tq, tk, tv, p, g2, stream);
+  }
   constexpr int NS = (D == 128) ? 3 : 6;
   // Q tile + NS x (K + V^T stage) + barriers = 112.1 KB -> exactly two CTAs (2 x 256 TMEM columns) fit the 228 KB of an SM
   size_t smem = size_t(BM) * D + size_t(NS) * 2 * LK * D + 256;

@@ -1,0 +1,85 @@
+// Shared declarations of the attention kernels (attn.cu: one Q tile per CTA, two CTAs per SM; attn_pair.cu: two Q tiles
+// per CTA with explicit exp ping-pong).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <type_traits>
+#include "common.cuh"
+#include "ptx.cuh"
+
+#ifdef SAB_TIMELINE
+#define SAB_TL(slot) do { if (tl_on && j >= 16 && j < 48) tl[(j - 16) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define SAB_TL(slot) do {} while (0)
+#endif
+
+namespace sab {
+
+constexpr int BM = 128;  // Q rows per CTA
+constexpr int BN = 64;   // keys per softmax / MMA tile (reference CTA_K)
+constexpr int LK = 128;  // keys per TMA stage (two tiles)
+constexpr uint32_t kTmemCols = 256;
+constexpr float kFp8Offset = 8.807f;      // attn_utils.cuh:30
+constexpr float kMaskValue = -5000000.0f; // attn_utils.cuh:310
+constexpr int kIntSentinel = -(1 << 30);
+constexpr int kAlphaCol = 16;  // column of an S buffer (beyond the 16 P columns) that carries alpha(j) to the correction warps
+
+struct AttnParams {
+  const float* q_scale;
+  const float* k_scale;
+  const float* v_scale;  // nullable
+  const float* v_mean;   // nullable
+  void* out;
+  float* lse;  // nullable
+  int64_t o_stride_b, o_stride_h, o_stride_s;
+  int B, Hq, Hkv, Sq, Sk;
+  int n_q_tiles;
+  int causal;
+  float sm_scale_log2;
+  int q_mult;            // scales per 128-row Q block: 1 / 4 / 32
+  int q_gran;            // 1 / 2 / 3
+  int k_mult;            // scales per 64-key block: 1 / 4
+  int64_t qs_stride_bh;  // dense: scales per (b,h); varlen: unused
+  int64_t ks_stride_bh;
+  int qs_stride_idx;     // dense 1, varlen Hq
+  int ks_stride_idx;     // dense 1, varlen Hkv
+  const int32_t* cu_q;   // varlen (nullable)
+  const int32_t* cu_k;
+  const int32_t* cu_v;
+  const int32_t* cu_qs;
+  const int32_t* cu_ks;
+  int causal_q_offset;   // global index of query row 0 (sequence-parallel causal)
+  int kv_seg_len;        // > 0: K/V are rank-major all-gathered segments of this many keys
+  int32_t* dbg;          // nullable debug dump (CTA 0 only)
+};
+
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+#ifdef SAB_WATCHDOG
+  // Debug build: bounded spin, a protocol bug traps (visible as a launch failure) instead of hanging the GPU.
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("sab: mbarrier timeout block(%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+
+}  // namespace sab

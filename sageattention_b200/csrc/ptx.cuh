@@ -56,6 +56,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
 __device__ __forceinline__ void setmaxnreg_inc_112() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;"); }
 __device__ __forceinline__ void setmaxnreg_dec_48() { asm volatile("setmaxnreg.dec.sync.aligned.u32 48;"); }
 
+// One elected lane of a fully converged warp (the surrounding code stays warp-uniform, so the compiler keeps UMMA
+// descriptors / addresses in uniform registers instead of paying R2UR round trips before every tcgen05 instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
