@@ -180,6 +180,29 @@ int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8, const uin
                            int max_seqlen_q, int causal_q_offset, int kv_seg_len, int32_t* debug_dump,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * FP16-PV variant: INT8 QK^T -> fp32 online softmax WITHOUT exponent offset -> FP16 P -> FP16 PV
+ * (tcgen05 kind::f16, fp32 accumulation in tensor memory).  Replaces the Triton attention launchers
+ * `forward` of sageattention/triton/attn_qk_int8_per_block.py:130-183, attn_qk_int8_per_block_causal.py,
+ * attn_qk_int8_block_varlen.py:123-150, attn_qk_int8_per_block_causal_varlen.py (the kernels behind
+ * sageattn_qk_int8_pv_fp16_triton and sageattn_varlen).  Arguments as sab_qk_int8_sv_f8_attn except:
+ *   v_f16t : [B,Hkv,D,s_pad] fp16 (token-contiguous, zero padded) from sab_v_transpose_f16;
+ *   no v_scale / v_mean (V is not quantised); no sequence-parallel form.
+ * sab_v_transpose_f16 replaces `v.to(torch.float16)` (sageattention/core.py:297-298) plus the K-major
+ * re-layout tcgen05 needs; varlen form as sab_per_channel_fp8.
+ * ---------------------------------------------------------------------------------------------- */
+int sab_v_transpose_f16(const void* v, int dtype, void* v_f16t, int B, int H, int S, int D, int64_t stride_b,
+                        int64_t stride_h, int64_t stride_s, int64_t s_pad, const int32_t* cu_seqlens,
+                        const int32_t* cu_pad, int nseq, int max_seqlen, void* stream);
+int sab_qk_int8_sv_f16_attn(const int8_t* q_int8, const int8_t* k_int8, const void* v_f16t, void* out, float* lse,
+                            const float* q_scale, const float* k_scale, int out_dtype, int B, int Hq, int Hkv,
+                            int Sq, int Skv, int D, int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
+                            int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_s, int64_t v_s_pad,
+                            int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s, int is_causal, int q_gran,
+                            int k_gran, float sm_scale, int fold_sm_scale, const int32_t* cu_seqlens_q,
+                            const int32_t* cu_seqlens_k, const int32_t* cu_pad_v, const int32_t* cu_q_scale,
+                            const int32_t* cu_k_scale, int max_seqlen_q, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,9 @@ EXPORTS = {
     "sab_channel_stats": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_int64] * 3 + [c_void_p, c_void_p]),
     "sab_v_quant_with_amax": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_int64] * 4 +
                               [c_float, c_void_p, c_void_p]),
+    "sab_v_transpose_f16": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_int64] * 4 + [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "sab_qk_int8_sv_f16_attn": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_int64] * 10 + [c_int, c_int, c_int, c_float, c_int] +
+                                [c_void_p] * 5 + [c_int, c_void_p]),
     "sab_qk_int8_sv_f8_attn": (c_int, [c_void_p] * 9 + [c_int] * 7 + [c_int64] * 10 + [c_int, c_int, c_int, c_float, c_int] +
                                [c_void_p] * 5 + [c_int, c_int, c_int, c_void_p, c_void_p]),
 }

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from . import ops
 from ._capi import SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_WARP, SAB_GRAN_PER_THREAD
 from .quant import (k_mean, per_block_int8, per_warp_int8, per_thread_int8, per_channel_fp8,
-                    per_block_int8_varlen, per_channel_fp8_varlen)
+                    per_block_int8_varlen, per_channel_fp8_varlen, transpose_v_f16, transpose_v_f16_varlen)
 
 _LOG2E = 1.44269504
 
@@ -137,10 +137,10 @@ def sageattn_qk_int8_pv_fp8_cuda_sm90(q, k, v, tensor_layout: str = "HND", is_ca
 def sageattn_qk_int8_pv_fp16_triton(q, k, v, tensor_layout: str = "HND", quantization_backend: str = "triton",
                                     is_causal: bool = False, sm_scale: Optional[float] = None, smooth_k: bool = True,
                                     return_lse: bool = False, attn_mask: Optional[torch.Tensor] = None, **kwargs: Any):
-    """API shell for sageattention/core.py:160-331: per-block INT8 quantisation with the Triton path's exact
-    rounding (bit-exact q/k/scales), sm_scale*log2e folded into q, attention on the sm_100a kernel.
-    PV runs in FP8 here (the reference uses FP16 PV), so outputs agree to FP8-P accuracy.  attn_mask is
-    not supported by the B200 kernel yet."""
+    """sageattention/core.py:160-331 on sm_100a: per-block INT8 quantisation with the Triton path's exact rounding
+    (bit-exact q/k/scales), sm_scale*log2e folded into q, then the FP16-PV kernel variant (tcgen05 kind::f16, P and
+    V in fp16, softmax without exponent offset — the Triton kernel's numerics, triton/attn_qk_int8_per_block.py).
+    attn_mask is not supported by the B200 kernel yet."""
     if attn_mask is not None:
         raise NotImplementedError("attn_mask is not supported by the sm_100a kernel yet")
     dtype = q.dtype
@@ -161,11 +161,10 @@ def sageattn_qk_int8_pv_fp16_triton(q, k, v, tensor_layout: str = "HND", quantiz
         raise ValueError(f"Unsupported quantization backend: {quantization_backend}")
     q_int8, q_scale, k_int8, k_scale = per_block_int8(q, k, km=km, sm_scale=sm_scale, tensor_layout=tensor_layout,
                                                       semantics=quantization_backend)
-    v_fp8, v_scale, _ = per_channel_fp8(v, tensor_layout=tensor_layout, scale_max=448.0, smooth_v=False)
+    v_t = transpose_v_f16(v, tensor_layout=tensor_layout)       # `v.to(torch.float16)`, core.py:297-298
     o = torch.empty(q.size(), dtype=dtype, device=q.device)
-    lse = ops.qk_int8_sv_f8_attn(q_int8, k_int8, v_fp8, o, q_scale, k_scale, v_scale, None, _tensor_layout,
-                                 1 if is_causal else 0, SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_BLOCK, sm_scale, 1,
-                                 1 if return_lse else 0)
+    lse = ops.qk_int8_sv_f16_attn(q_int8, k_int8, v_t, o, q_scale, k_scale, _tensor_layout, 1 if is_causal else 0,
+                                  SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_BLOCK, sm_scale, 1, 1 if return_lse else 0)
     o = o[..., :head_dim_og]
     if return_lse:
         return o, lse / _LOG2E + lse_correction * sm_scale if smooth_k else lse / _LOG2E
@@ -187,8 +186,8 @@ def sageattn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlen
                     cu_seqlens_k: torch.Tensor, max_seqlen_q: int, max_seqlen_k: int, is_causal: bool = False,
                     sm_scale: Optional[float] = None, smooth_k: bool = True, **kwargs: Any) -> torch.Tensor:
     """sageattention/core.py:334-448: packed [T,H,D] tensors, per-block INT8 per sequence (Triton rounding,
-    bit-exact), K mean over all tokens of the batch (core.py:433).  PV runs in FP8 on the sm_100a kernel
-    (the reference's Triton kernel uses FP16 PV)."""
+    bit-exact), K mean over all tokens of the batch (core.py:433), FP16 P and V (tcgen05 kind::f16) like the
+    reference's Triton varlen kernels."""
     dtype = q.dtype
     _check_inputs(q, k, v)
     q, k, v, head_dim_og = _pad_head_dim(q, k, v)
@@ -201,9 +200,9 @@ def sageattn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlen
         sm_scale = 1.0 / (head_dim_og ** 0.5)
     q_int8, q_scale, k_int8, k_scale, cu_q_scale, cu_k_scale = per_block_int8_varlen(
         q, k, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k, sm_scale=sm_scale, km=km)
-    v_fp8, v_scale, cu_pad = per_channel_fp8_varlen(v, cu_seqlens_k, max_seqlen_k, scale_max=448.0)
+    v_t, cu_pad = transpose_v_f16_varlen(v, cu_seqlens_k, max_seqlen_k)
     o = torch.empty(q.shape, dtype=dtype, device=q.device)
-    ops.qk_int8_sv_f8_attn_varlen(q_int8, k_int8, v_fp8, o, q_scale, k_scale, v_scale,
-                                  cu_seqlens_q.to(torch.int32), cu_seqlens_k.to(torch.int32), cu_pad, cu_q_scale,
-                                  cu_k_scale, max_seqlen_q, 1 if is_causal else 0, sm_scale, 1)
+    ops.qk_int8_sv_f16_attn_varlen(q_int8, k_int8, v_t, o, q_scale, k_scale, cu_seqlens_q.to(torch.int32),
+                                   cu_seqlens_k.to(torch.int32), cu_pad, cu_q_scale, cu_k_scale, max_seqlen_q,
+                                   1 if is_causal else 0, sm_scale, 1)
     return o[..., :head_dim_og]

@@ -24,15 +24,21 @@ namespace sab {
 constexpr int kNumThreads = 384;  // warpgroups: 0-3 softmax, 4-7 correction, 8 TMA / 9 MMA / 10-11 idle (setmaxnreg is per warpgroup)
 
 // D: head dim (64 / 128).  kKT: per-thread K scales (4 per 64-key block) instead of 1.  OutT: __half / bf16.
-template <int D, bool kKT, typename OutT>
+// kPV16: P and V in fp16 (tcgen05 kind::f16) with the Triton path's softmax (no exponent offset) — the numerics of the
+// reference's sageattn_qk_int8_pv_fp16_triton / sageattn_varlen kernels (triton/attn_qk_int8_per_block.py:22-128).
+template <int D, bool kKT, typename OutT, bool kPV16>
 __global__ void __launch_bounds__(kNumThreads, 2)
 sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  constexpr int NS = (D == 128) ? 3 : 6;      // K/V ring depth (128-key stages)
+  constexpr int NS = kPV16 ? ((D == 128) ? 2 : 4) : ((D == 128) ? 3 : 6);   // K/V ring depth (128-key stages)
   constexpr int SWQK = (D == 128) ? 128 : 64; // swizzle span of the Q/K tiles (= row bytes)
-  constexpr uint32_t Q_BYTES = BM * D, K_BYTES = LK * D, V_BYTES = D * LK;
+  constexpr uint32_t VT_BYTES = D * BN * (kPV16 ? 2 : 1);   // one 64-key V^T tile: D rows x 64 keys
+  constexpr uint32_t Q_BYTES = BM * D, K_BYTES = LK * D, V_BYTES = 2 * VT_BYTES;
   constexpr uint64_t K_HALF = (uint64_t(BN) * D) >> 4;  // descriptor delta: keys 64..127 of a K stage
-  constexpr uint64_t V_HALF = uint64_t(BN) >> 4;        // descriptor delta: byte column 64 of a V^T stage
+  // descriptor delta of the second 64-key tile of a V^T stage: fp8 = byte column 64 of the same 128-byte rows;
+  // fp16 = a separate [D x 128 B] tile (a 64-key fp16 row already fills the 128-byte swizzle span)
+  constexpr uint64_t V_HALF = kPV16 ? (uint64_t(VT_BYTES) >> 4) : (uint64_t(BN) >> 4);
+  constexpr int PCOLS = kPV16 ? 32 : 16;                // TMEM columns of P (64 keys)
   constexpr int NG = kKT ? 4 : 1;                       // dequant-scale groups per 64-key tile
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -121,7 +127,12 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_wait_wd(kv_empty + s, ph ^ 1);
           mbar_expect_tx(kv_full + s, K_BYTES + V_BYTES);
           tma_load_4d(sK + s * K_BYTES, &tmK, kv_full + s, 0, kc, hk, kb);
-          tma_load_4d(sV + s * V_BYTES, &tmV, kv_full + s, vc, 0, hk, kb);
+          if constexpr (kPV16) {   // byte coordinates: 2 bytes per key
+            tma_load_4d(sV + s * V_BYTES, &tmV, kv_full + s, vc * 2, 0, hk, kb);
+            tma_load_4d(sV + s * V_BYTES + VT_BYTES, &tmV, kv_full + s, (vc + BN) * 2, 0, hk, kb);
+          } else {
+            tma_load_4d(sV + s * V_BYTES, &tmV, kv_full + s, vc, 0, hk, kb);
+          }
         }
       }
     } else if (warp == 9) {
@@ -168,7 +179,11 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint32_t tP = tmem_u + (j & 1) * BN;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tmem_u + 128, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
+            if constexpr (kPV16) {
+              for (int k = 0; k < BN / 16; ++k) umma_f16_ts(tmem_u + 128, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
+            } else {
+              for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tmem_u + 128, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
+            }
           }
           SAB_TL(10);
           if (j + 2 < n_kv) issue_qk(j + 2);               // reuses S buffer j&1 (after PV(j): in-order pipe)
@@ -296,7 +311,8 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if constexpr (MASKED) c = (v == kIntSentinel) ? kMaskValue : c;
           mx = fmaxf(mx, c);
         }
-        const float m_new = fmaxf(m, mx - kFp8Offset);  // update_mdo, attn_utils.cuh:377-396
+        // fp8 P: update_mdo with the -log2(448) offset (attn_utils.cuh:377-396); fp16 P: plain running max (Triton path)
+        const float m_new = fmaxf(m, kPV16 ? mx : mx - kFp8Offset);
         const float alpha = ex2_approx(m - m_new);
         d *= alpha;
         m = m_new;
@@ -318,7 +334,7 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int g = 0; g < NG; ++g) coef2[g] = pack_f2(coef[g], coef[g]);
         const uint64_t nm2 = pack_f2(nm, nm);
         uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
-        uint32_t pk[BN / 4];
+        uint32_t pk[PCOLS];
 #pragma unroll
         for (int w = 0; w < BN / 4; ++w) {
           float e[4];
@@ -341,7 +357,12 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             acc[(w & 1) * 2 + (u >> 1)] = fadd2(acc[(w & 1) * 2 + (u >> 1)], pack_f2(e[u], e[u + 1]));
           }
-          pk[w] = pack_e4m3x4(e[0], e[1], e[2], e[3]);
+          if constexpr (kPV16) {
+            pk[2 * w] = pack_f16x2(e[0], e[1]);       // p.to(tl.float16), attn_qk_int8_per_block.py:62
+            pk[2 * w + 1] = pack_f16x2(e[2], e[3]);
+          } else {
+            pk[w] = pack_e4m3x4(e[0], e[1], e[2], e[3]);
+          }
         }
         {
           float a0, a1, a2, a3;
@@ -350,8 +371,9 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           d += (a0 + a1) + (a2 + a3);
         }
         SAB_TL(4);
-        tmem_st16(tS, pk);
-        if (dump && j == 0) {
+        if constexpr (kPV16) tmem_st32(tS, pk);
+        else tmem_st16(tS, pk);
+        if (!kPV16 && dump && j == 0) {
 #pragma unroll
           for (int w = 0; w < BN / 4; ++w) p.dbg[128 * BN + row * 16 + w] = int(pk[w]);
         }
@@ -483,18 +505,18 @@ static bool use_pair_kernel() {
   return v == 1;
 }
 
-template <int D, bool kKT, typename OutT>
+template <int D, bool kKT, typename OutT, bool kPV16>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  if (use_pair_kernel()) {
+  if (!kPV16 && use_pair_kernel()) {
     dim3 g2((grid.x + 1) / 2, grid.y, grid.z);
     return launch_attn_pair<D, kKT, OutT>(tq, tk, tv, p, g2, stream);
   }
-  constexpr int NS = (D == 128) ? 3 : 6;
+  constexpr int NS = kPV16 ? ((D == 128) ? 2 : 4) : ((D == 128) ? 3 : 6);
   // Q tile + NS x (K + V^T stage) + barriers = 112.1 KB -> exactly two CTAs (2 x 256 TMEM columns) fit the 228 KB of an SM
-  size_t smem = size_t(BM) * D + size_t(NS) * 2 * LK * D + 256;
+  size_t smem = size_t(BM) * D + size_t(NS) * (LK * D + LK * D * (kPV16 ? 2 : 1)) + 256;
   if (smem < 80 * 1024) smem = 80 * 1024;
-  auto kern = sage_attn_fwd_kernel<D, kKT, OutT>;
+  auto kern = sage_attn_fwd_kernel<D, kKT, OutT, kPV16>;
   static bool configured = false;
   if (!configured) {
     SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -507,7 +529,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 
 }  // namespace sab
 
-extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8, const uint8_t* v_fp8, void* out,
+static int attn_entry(int pv16, const int8_t* q_int8, const int8_t* k_int8, const uint8_t* v_fp8, void* out,
                                       float* lse, const float* q_scale, const float* k_scale, const float* v_scale,
                                       const float* v_mean, int out_dtype, int B, int Hq, int Hkv, int Sq, int Skv,
                                       int D, int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
@@ -524,6 +546,7 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
   SAB_REQUIRE(out_dtype == SAB_DTYPE_FP16 || out_dtype == SAB_DTYPE_BF16, SAB_ERR_UNSUPPORTED, "output dtype must be fp16 or bf16");
   SAB_REQUIRE(B > 0 && Hq > 0 && Hkv > 0 && Sq > 0 && Skv >= 0, SAB_ERR_INVALID, "bad sizes B=%d Hq=%d Hkv=%d Sq=%d Skv=%d", B, Hq, Hkv, Sq, Skv);
   SAB_REQUIRE(Hq % Hkv == 0, SAB_ERR_INVALID, "num_qo_heads (%d) must be divisible by num_kv_heads (%d)", Hq, Hkv);
+  const uint64_t vb = pv16 ? 2 : 1;   // bytes per V element
   SAB_REQUIRE(q_gran >= 1 && q_gran <= 3 && k_gran >= 1 && k_gran <= 3, SAB_ERR_INVALID, "unknown quant granularity q=%d k=%d", q_gran, k_gran);
   SAB_REQUIRE(v_s_pad % 128 == 0 && (v_s_pad >= Skv || kv_seg_len > 0), SAB_ERR_INVALID, "v_fp8 token dimension (%lld) must be a multiple of 128 and >= kv_len", (long long)v_s_pad);
   SAB_REQUIRE(aligned16(out) && o_stride_s % 8 == 0 && o_stride_h % 8 == 0 && o_stride_b % 8 == 0, SAB_ERR_INVALID, "output must be 16-byte aligned with strides multiple of 8 elements");
@@ -543,16 +566,16 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
     const int P = Skv / kv_seg_len;
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, B, q_stride_s, q_stride_h, q_stride_b, D, BM, swqk))) return st;
     if ((st = make_map_u8(&tk, k_int8, D, kv_seg_len, Hkv, uint64_t(B) * P, k_stride_s, k_stride_h, k_stride_b, D, LK, swqk))) return st;
-    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, uint64_t(B) * P, v_s_pad, uint64_t(v_s_pad) * D, uint64_t(v_s_pad) * D * Hkv, LK, D, 128))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad * vb, D, Hkv, uint64_t(B) * P, v_s_pad * vb, uint64_t(v_s_pad) * D * vb, uint64_t(v_s_pad) * D * Hkv * vb, LK, D, 128))) return st;
   } else if (!varlen) {
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, B, q_stride_s, q_stride_h, q_stride_b, D, BM, swqk))) return st;
     if ((st = make_map_u8(&tk, k_int8, D, Skv > 0 ? Skv : 1, Hkv, B, k_stride_s, k_stride_h, k_stride_b, D, LK, swqk))) return st;
-    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, B, v_s_pad, uint64_t(v_s_pad) * D, uint64_t(v_s_pad) * D * Hkv, LK, D, 128))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad * vb, D, Hkv, B, v_s_pad * vb, uint64_t(v_s_pad) * D * vb, uint64_t(v_s_pad) * D * Hkv * vb, LK, D, 128))) return st;
   } else {
     // packed [T,H,D]: Sq / Skv are the TOTAL token counts
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, 1, q_stride_s, q_stride_h, 0, D, BM, swqk))) return st;
     if ((st = make_map_u8(&tk, k_int8, D, Skv, Hkv, 1, k_stride_s, k_stride_h, 0, D, LK, swqk))) return st;
-    if ((st = make_map_u8(&tv, v_fp8, v_s_pad, D, Hkv, 1, v_s_pad, uint64_t(v_s_pad) * D, 0, LK, D, 128))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad * vb, D, Hkv, 1, v_s_pad * vb, uint64_t(v_s_pad) * D * vb, 0, LK, D, 128))) return st;
   }
 
   AttnParams p{};
@@ -579,7 +602,11 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool kt = k_gran == SAB_GRAN_PER_THREAD;
   const bool bf = out_dtype == SAB_DTYPE_BF16;
-#define SAB_LAUNCH(DD, KT, T) return launch_attn<DD, KT, T>(tq, tk, tv, p, grid, s)
+#define SAB_LAUNCH(DD, KT, T)                                                      \
+  do {                                                                             \
+    if (pv16) return launch_attn<DD, KT, T, true>(tq, tk, tv, p, grid, s);         \
+    return launch_attn<DD, KT, T, false>(tq, tk, tv, p, grid, s);                  \
+  } while (0)
   if (D == 128) {
     if (kt) { if (bf) SAB_LAUNCH(128, true, __nv_bfloat16); else SAB_LAUNCH(128, true, __half); }
     else    { if (bf) SAB_LAUNCH(128, false, __nv_bfloat16); else SAB_LAUNCH(128, false, __half); }
@@ -588,4 +615,35 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
     else    { if (bf) SAB_LAUNCH(64, false, __nv_bfloat16); else SAB_LAUNCH(64, false, __half); }
   }
 #undef SAB_LAUNCH
+}
+
+extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8, const uint8_t* v_fp8, void* out,
+                                      float* lse, const float* q_scale, const float* k_scale, const float* v_scale,
+                                      const float* v_mean, int out_dtype, int B, int Hq, int Hkv, int Sq, int Skv,
+                                      int D, int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
+                                      int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_s, int64_t v_s_pad,
+                                      int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s, int is_causal,
+                                      int q_gran, int k_gran, float sm_scale, int fold_sm_scale,
+                                      const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k,
+                                      const int32_t* cu_pad_v, const int32_t* cu_q_scale, const int32_t* cu_k_scale,
+                                      int max_seqlen_q, int causal_q_offset, int kv_seg_len, int32_t* debug_dump,
+                                      void* stream) {
+  return attn_entry(0, q_int8, k_int8, v_fp8, out, lse, q_scale, k_scale, v_scale, v_mean, out_dtype, B, Hq, Hkv, Sq, Skv, D,
+                    q_stride_b, q_stride_h, q_stride_s, k_stride_b, k_stride_h, k_stride_s, v_s_pad, o_stride_b, o_stride_h,
+                    o_stride_s, is_causal, q_gran, k_gran, sm_scale, fold_sm_scale, cu_seqlens_q, cu_seqlens_k, cu_pad_v,
+                    cu_q_scale, cu_k_scale, max_seqlen_q, causal_q_offset, kv_seg_len, debug_dump, stream);
+}
+
+extern "C" int sab_qk_int8_sv_f16_attn(const int8_t* q_int8, const int8_t* k_int8, const void* v_f16t, void* out, float* lse,
+                                       const float* q_scale, const float* k_scale, int out_dtype, int B, int Hq, int Hkv,
+                                       int Sq, int Skv, int D, int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
+                                       int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_s, int64_t v_s_pad,
+                                       int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s, int is_causal, int q_gran,
+                                       int k_gran, float sm_scale, int fold_sm_scale, const int32_t* cu_seqlens_q,
+                                       const int32_t* cu_seqlens_k, const int32_t* cu_pad_v, const int32_t* cu_q_scale,
+                                       const int32_t* cu_k_scale, int max_seqlen_q, void* stream) {
+  return attn_entry(1, q_int8, k_int8, reinterpret_cast<const uint8_t*>(v_f16t), out, lse, q_scale, k_scale, nullptr, nullptr,
+                    out_dtype, B, Hq, Hkv, Sq, Skv, D, q_stride_b, q_stride_h, q_stride_s, k_stride_b, k_stride_h, k_stride_s,
+                    v_s_pad, o_stride_b, o_stride_h, o_stride_s, is_causal, q_gran, k_gran, sm_scale, fold_sm_scale,
+                    cu_seqlens_q, cu_seqlens_k, cu_pad_v, cu_q_scale, cu_k_scale, max_seqlen_q, 0, 0, nullptr, stream);
 }

@@ -22,7 +22,7 @@ constexpr uint32_t kTmemCols = 256;
 constexpr float kFp8Offset = 8.807f;      // attn_utils.cuh:30
 constexpr float kMaskValue = -5000000.0f; // attn_utils.cuh:310
 constexpr int kIntSentinel = -(1 << 30);
-constexpr int kAlphaCol = 16;  // column of an S buffer (beyond the 16 P columns) that carries alpha(j) to the correction warps
+constexpr int kAlphaCol = 40;  // column of an S buffer (beyond the 16 / 32 P columns) that carries alpha(j) to the correction warps
 
 struct AttnParams {
   const float* q_scale;

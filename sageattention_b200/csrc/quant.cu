@@ -331,6 +331,46 @@ __global__ void __launch_bounds__(256) v_quant_transpose_kernel(const VQuantPara
   }
 }
 
+// V -> fp16, transposed to [.., D, S_pad] (token-contiguous), zero padded: the B operand of the kind::f16 PV MMA
+// (`v.to(torch.float16)`, sageattention/core.py:297-298, + the K-major layout tcgen05 wants).
+template <typename T, int D>
+__global__ void __launch_bounds__(256) v_transpose_f16_kernel(const VQuantParams p) {
+  constexpr int TPR = D / 8;
+  constexpr int RPP = 256 / TPR;
+  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  int S = p.S, tok0 = 0;
+  int64_t col0 = int64_t(tile) * 128;
+  const bool varlen = p.cu != nullptr;
+  if (varlen) {
+    tok0 = p.cu[b];
+    S = p.cu[b + 1] - tok0;
+    if (tile * 128 >= S) return;
+    col0 += p.cu_pad[b];
+  }
+  __shared__ __align__(16) T s_in[128][D + 8];
+  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
+  const T* vb = reinterpret_cast<const T*>(p.v) + (varlen ? int64_t(tok0) * p.ss : int64_t(b) * p.sb) + int64_t(h) * p.sh + tc * 8;
+#pragma unroll
+  for (int r = tr; r < 128; r += RPP) {
+    const int row = tile * 128 + r;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (row < S) raw = *reinterpret_cast<const uint4*>(vb + int64_t(row) * p.ss);
+    *reinterpret_cast<uint4*>(&s_in[r][tc * 8]) = raw;
+  }
+  __syncthreads();
+  const int bh = (varlen ? 0 : b) * p.H + h;
+  __half* out = reinterpret_cast<__half*>(p.out);
+  for (int task = threadIdx.x; task < D * 8; task += 256) {   // (channel d, 16-token segment): 32 bytes per thread
+    const int d = task % D, seg = task / D;
+    __half hv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hv[i] = __float2half_rn(to_f<T>(s_in[seg * 16 + i][d]));
+    uint4* dst = reinterpret_cast<uint4*>(out + (int64_t(bh) * D + d) * p.s_pad + col0 + seg * 16);
+    dst[0] = reinterpret_cast<uint4*>(hv)[0];
+    dst[1] = reinterpret_cast<uint4*>(hv)[1];
+  }
+}
+
 static int check_common(const void* x, int dtype, int D, int64_t s0, int64_t s1, int64_t s2) {
   SAB_REQUIRE(x != nullptr, SAB_ERR_INVALID, "null input pointer");
   SAB_REQUIRE(dtype == SAB_DTYPE_FP16 || dtype == SAB_DTYPE_BF16, SAB_ERR_UNSUPPORTED, "Only half and bfloat16 are supported");
@@ -521,6 +561,29 @@ extern "C" int sab_v_quant_with_amax(const void* v, int dtype, uint8_t* v_fp8, c
   if (dtype == SAB_DTYPE_FP16) { if (D == 128) SAB_VQ(__half, 128); else SAB_VQ(__half, 64); }
   else { if (D == 128) SAB_VQ(__nv_bfloat16, 128); else SAB_VQ(__nv_bfloat16, 64); }
 #undef SAB_VQ
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
+}
+
+extern "C" int sab_v_transpose_f16(const void* v, int dtype, void* v_f16t, int B, int H, int S, int D, int64_t stride_b,
+                                   int64_t stride_h, int64_t stride_s, int64_t s_pad, const int32_t* cu_seqlens,
+                                   const int32_t* cu_pad, int nseq, int max_seqlen, void* stream) {
+  int st = check_common(v, dtype, D, cu_seqlens ? 0 : stride_b, stride_h, stride_s);
+  if (st) return st;
+  SAB_REQUIRE(v_f16t && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_v_transpose_f16");
+  SAB_REQUIRE(s_pad % 128 == 0 && aligned16(v_f16t), SAB_ERR_INVALID, "s_pad must be a multiple of 128 and the output 16-byte aligned");
+  const bool varlen = cu_seqlens != nullptr;
+  if (varlen) SAB_REQUIRE(cu_pad && nseq > 0 && max_seqlen > 0, SAB_ERR_INVALID, "varlen needs cu_pad, nseq, max_seqlen");
+  else SAB_REQUIRE(s_pad >= S && B > 0, SAB_ERR_INVALID, "s_pad < S");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  VQuantParams p{};
+  p.v = v; p.out = reinterpret_cast<uint8_t*>(v_f16t); p.H = H; p.S = S;
+  p.sb = stride_b; p.sh = stride_h; p.ss = stride_s; p.s_pad = s_pad; p.cu = cu_seqlens; p.cu_pad = cu_pad;
+  dim3 grid(varlen ? (max_seqlen + 127) / 128 : int(s_pad / 128), H, varlen ? nseq : B);
+#define SAB_VT(T, DD) v_transpose_f16_kernel<T, DD><<<grid, 256, 0, s>>>(p)
+  if (dtype == SAB_DTYPE_FP16) { if (D == 128) SAB_VT(__half, 128); else SAB_VT(__half, 64); }
+  else { if (D == 128) SAB_VT(__nv_bfloat16, 128); else SAB_VT(__nv_bfloat16, 64); }
+#undef SAB_VT
   SAB_CUDA_OK(cudaGetLastError());
   return SAB_OK;
 }

@@ -231,3 +231,87 @@ def qk_int8_sv_f8_attn_varlen(query: torch.Tensor, key: torch.Tensor, value: tor
 def _(query, key, value, output, query_scale, key_scale, value_scale, cu_seqlens_q, cu_seqlens_k, cu_pad_v,
       cu_q_scale, cu_k_scale, max_seqlen_q, is_causal, sm_scale, fold_sm_scale):
     return None
+
+
+# ----------------------------------------------------------------------------------------------- FP16-PV variant
+@torch.library.custom_op("sageattention_b200::v_transpose_f16", mutates_args=("v_f16t",), device_types="cuda")
+def v_transpose_f16(v: torch.Tensor, v_f16t: torch.Tensor, tensor_layout: int) -> None:
+    B, H, S, D = _bhsd(v, tensor_layout)
+    sb, sh, ss = _bhs_strides(v, tensor_layout)
+    with torch.cuda.device(v.device):
+        check(lib().sab_v_transpose_f16(v.data_ptr(), _dt(v), v_f16t.data_ptr(), B, H, S, D, sb, sh, ss, v_f16t.size(-1),
+                                        None, None, 0, 0, _stream(v)))
+
+
+@v_transpose_f16.register_fake
+def _(v, v_f16t, tensor_layout):
+    return None
+
+
+@torch.library.custom_op("sageattention_b200::v_transpose_f16_varlen", mutates_args=("v_f16t",), device_types="cuda")
+def v_transpose_f16_varlen(v: torch.Tensor, v_f16t: torch.Tensor, cu_seqlens: torch.Tensor, cu_pad: torch.Tensor,
+                           max_seqlen: int) -> None:
+    T, H, D = v.shape
+    with torch.cuda.device(v.device):
+        check(lib().sab_v_transpose_f16(v.data_ptr(), _dt(v), v_f16t.data_ptr(), 1, H, T, D, 0, v.stride(1), v.stride(0),
+                                        v_f16t.size(-1), cu_seqlens.data_ptr(), cu_pad.data_ptr(), cu_seqlens.numel() - 1,
+                                        max_seqlen, _stream(v)))
+
+
+@v_transpose_f16_varlen.register_fake
+def _(v, v_f16t, cu_seqlens, cu_pad, max_seqlen):
+    return None
+
+
+@torch.library.custom_op("sageattention_b200::qk_int8_sv_f16_attn", mutates_args=("output",), device_types="cuda")
+def qk_int8_sv_f16_attn(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, output: torch.Tensor,
+                        query_scale: torch.Tensor, key_scale: torch.Tensor, tensor_layout: int, is_causal: int,
+                        q_quant_gran: int, k_quant_gran: int, sm_scale: float, fold_sm_scale: int,
+                        return_lse: int) -> torch.Tensor:
+    """INT8 QK^T + FP16 PV (the reference Triton kernels' numerics); value = [B,Hkv,D,S_pad] fp16 from v_transpose_f16."""
+    B, Hq, Sq, D = _bhsd(query, tensor_layout)
+    _, Hkv, Skv, _ = _bhsd(key, tensor_layout)
+    qs, ks, os_ = _bhs_strides(query, tensor_layout), _bhs_strides(key, tensor_layout), _bhs_strides(output, tensor_layout)
+    lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=query.device) if return_lse else \
+        torch.empty((0,), dtype=torch.float32, device=query.device)
+    with torch.cuda.device(query.device):
+        check(lib().sab_qk_int8_sv_f16_attn(query.data_ptr(), key.data_ptr(), value.data_ptr(), output.data_ptr(),
+                                            lse.data_ptr() if return_lse else None, query_scale.data_ptr(), key_scale.data_ptr(),
+                                            _dt(output), B, Hq, Hkv, Sq, Skv, D, *qs, *ks, value.size(-1), *os_, is_causal,
+                                            q_quant_gran, k_quant_gran, float(sm_scale), fold_sm_scale, None, None, None, None,
+                                            None, 0, _stream(query)))
+    return lse
+
+
+@qk_int8_sv_f16_attn.register_fake
+def _(query, key, value, output, query_scale, key_scale, tensor_layout, is_causal, q_quant_gran, k_quant_gran, sm_scale,
+      fold_sm_scale, return_lse):
+    B, Hq, Sq, D = _bhsd(query, tensor_layout)
+    if return_lse:
+        return torch.empty((B, Hq, Sq), dtype=torch.float32, device=query.device)
+    return torch.empty((0,), dtype=torch.float32, device=query.device)
+
+
+@torch.library.custom_op("sageattention_b200::qk_int8_sv_f16_attn_varlen", mutates_args=("output",), device_types="cuda")
+def qk_int8_sv_f16_attn_varlen(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, output: torch.Tensor,
+                               query_scale: torch.Tensor, key_scale: torch.Tensor, cu_seqlens_q: torch.Tensor,
+                               cu_seqlens_k: torch.Tensor, cu_pad_v: torch.Tensor, cu_q_scale: torch.Tensor,
+                               cu_k_scale: torch.Tensor, max_seqlen_q: int, is_causal: int, sm_scale: float,
+                               fold_sm_scale: int) -> None:
+    Tq, Hq, D = query.shape
+    Tk, Hkv, _ = key.shape
+    nseq = cu_seqlens_q.numel() - 1
+    with torch.cuda.device(query.device):
+        check(lib().sab_qk_int8_sv_f16_attn(query.data_ptr(), key.data_ptr(), value.data_ptr(), output.data_ptr(), None,
+                                            query_scale.data_ptr(), key_scale.data_ptr(), _dt(output), nseq, Hq, Hkv, Tq, Tk, D,
+                                            0, query.stride(1), query.stride(0), 0, key.stride(1), key.stride(0), value.size(-1),
+                                            0, output.stride(1), output.stride(0), is_causal, _capi.SAB_GRAN_PER_BLOCK,
+                                            _capi.SAB_GRAN_PER_BLOCK, float(sm_scale), fold_sm_scale, cu_seqlens_q.data_ptr(),
+                                            cu_seqlens_k.data_ptr(), cu_pad_v.data_ptr(), cu_q_scale.data_ptr(),
+                                            cu_k_scale.data_ptr(), max_seqlen_q, _stream(query)))
+
+
+@qk_int8_sv_f16_attn_varlen.register_fake
+def _(query, key, value, output, query_scale, key_scale, cu_seqlens_q, cu_seqlens_k, cu_pad_v, cu_q_scale, cu_k_scale,
+      max_seqlen_q, is_causal, sm_scale, fold_sm_scale):
+    return None

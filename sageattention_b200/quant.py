@@ -153,3 +153,26 @@ def per_channel_fp8_varlen(v: torch.Tensor, cu_seqlens_k: torch.Tensor, max_seql
     v_scale = torch.empty((h_kv, head_dim), dtype=torch.float32, device=v.device)
     ops.per_channel_fp8_varlen(v, v_fp8, v_scale, cu32, cu_pad, max_seqlen_k, scale_max)
     return v_fp8, v_scale, cu_pad
+
+
+def transpose_v_f16(v: torch.Tensor, tensor_layout: str = "HND") -> torch.Tensor:
+    """`v.to(torch.float16)` (sageattention/core.py:297-298) in the layout the kind::f16 PV MMA consumes:
+    ``[B, H_kv, D, ceil(kv_len/128)*128]`` fp16, token-contiguous, zero padded."""
+    b, h_kv, kv_len, head_dim = _dims(v, tensor_layout)
+    padded_len = (kv_len + 127) // 128 * 128
+    v_t = torch.empty((b, h_kv, head_dim, padded_len), dtype=torch.float16, device=v.device)
+    ops.v_transpose_f16(v, v_t, _layout(tensor_layout))
+    return v_t
+
+
+def transpose_v_f16_varlen(v: torch.Tensor, cu_seqlens_k: torch.Tensor, max_seqlen_k: int):
+    """Packed form: v [T,H,D] -> [H, D, T_pad] fp16 with every sequence padded to 128 tokens; returns (v_t, cu_pad)."""
+    T, h_kv, head_dim = v.shape
+    cu32 = cu_seqlens_k.to(torch.int32)
+    lens = cu32[1:] - cu32[:-1]
+    cu_pad = torch.nn.functional.pad(torch.cumsum((lens + 127) // 128 * 128, dim=0), (1, 0), value=0).to(torch.int32)
+    nseq = cu32.numel() - 1
+    t_pad = (T + 127 * nseq + 127) // 128 * 128
+    v_t = torch.empty((h_kv, head_dim, t_pad), dtype=torch.float16, device=v.device)
+    ops.v_transpose_f16_varlen(v, v_t, cu32, cu_pad, max_seqlen_k)
+    return v_t, cu_pad
