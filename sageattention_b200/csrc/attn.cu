@@ -30,27 +30,27 @@ template <int D, bool kKT, typename OutT, bool kPV16>
 __global__ void __launch_bounds__(kNumThreads, 2)
 sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  constexpr int NS = kPV16 ? ((D == 128) ? 2 : 4) : ((D == 128) ? 3 : 6);   // K/V ring depth (128-key stages)
-  constexpr int SWQK = (D == 128) ? 128 : 64; // swizzle span of the Q/K tiles (= row bytes)
-  constexpr uint32_t VT_BYTES = D * BN * (kPV16 ? 2 : 1);   // one 64-key V^T tile: D rows x 64 keys
-  constexpr uint32_t Q_BYTES = BM * D, K_BYTES = LK * D, V_BYTES = 2 * VT_BYTES;
-  constexpr uint64_t K_HALF = (uint64_t(BN) * D) >> 4;  // descriptor delta: keys 64..127 of a K stage
-  // descriptor delta of the second 64-key tile of a V^T stage: fp8 = byte column 64 of the same 128-byte rows;
-  // fp16 = a separate [D x 128 B] tile (a 64-key fp16 row already fills the 128-byte swizzle span)
-  constexpr uint64_t V_HALF = kPV16 ? (uint64_t(VT_BYTES) >> 4) : (uint64_t(BN) >> 4);
-  constexpr int PCOLS = kPV16 ? 32 : 16;                // TMEM columns of P (64 keys)
-  constexpr int NG = kKT ? 4 : 1;                       // dequant-scale groups per 64-key tile
+  // K / V^T ring: one slot = one 64-key tile (K tile 64 x D bytes + V^T tile D rows x 64 keys)
+  constexpr uint32_t K_TILE = BN * D;
+  constexpr uint32_t V_TILE = D * BN * (kPV16 ? 2 : 1);
+  constexpr int NS = kPV16 ? ((D == 128) ? 3 : 6) : ((D == 128) ? 5 : 10);
+  constexpr int SWQK = (D == 128) ? 128 : 64;   // swizzle span of the Q/K tiles (= row bytes)
+  constexpr int SWV = kPV16 ? 128 : 64;          // V^T rows: 64 keys = 64 B (fp8) / 128 B (fp16)
+  constexpr uint32_t Q_BYTES = BM * D;
+  constexpr int PCOLS = kPV16 ? 32 : 16;         // TMEM columns of P (64 keys)
+  constexpr int NG = kKT ? 4 : 1;                // dequant-scale groups per 64-key tile
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;
-  uint8_t* sV = sK + NS * K_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * V_BYTES);
+  uint8_t* sV = sK + NS * K_TILE;
+  float* s_alpha = reinterpret_cast<float*>(sV + NS * V_TILE);   // [2][128] alpha(j): softmax -> correction warps
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_alpha + 2 * BM);
   uint64_t* q_full = bars + 0;
   uint64_t* s_full = bars + 1;    // [2] step(t) retired: S(t+2) ready in buffer t&1 AND PV(t) accumulated into O
   uint64_t* p_full = bars + 3;    // [2] 256 arrivals: P(j) stored (softmax) + O rescaled (correction)
   uint64_t* a_full = bars + 5;    // [2] 128 arrivals: alpha(j) published by the softmax warps
-  uint64_t* kv_full = bars + 7;   // [NS] TMA bytes landed (K + V^T of a 128-key stage)
+  uint64_t* kv_full = bars + 7;   // [NS] TMA bytes landed (K + V^T tile)
   uint64_t* kv_empty = kv_full + NS;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(kv_empty + NS);
 
@@ -79,7 +79,6 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   int n_kv = (kv_len + BN - 1) / BN;                 // 64-key tiles
   if (p.causal) n_kv = min(n_kv, (p.causal_q_offset + (qt + 1) * BM + BN - 1) / BN);
-  const int n_st = (n_kv + 1) / 2;                   // 128-key TMA stages
 
   // ---------------- one-time setup
   if (warp == 8 && lane == 0) {
@@ -115,24 +114,19 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (lane == 0 && n_kv > 0) {
         mbar_expect_tx(q_full, Q_BYTES);
         tma_load_4d(sQ, &tmQ, q_full, 0, q_off + qt * BM, h, tb);
-        for (int jj = 0; jj < n_st; ++jj) {
-          const int s = jj % NS;
-          const uint32_t ph = (jj / NS) & 1;
-          int kc = k_off + jj * LK, vc = v_off + jj * LK, kb = tb;
+        for (int j = 0; j < n_kv; ++j) {
+          const int s = j % NS;
+          const uint32_t ph = (j / NS) & 1;
+          int kc = k_off + j * BN, vc = v_off + j * BN, kb = tb;
           if (p.kv_seg_len > 0) {  // all-gathered layout: segment-major
-            const int seg = (jj * LK) / p.kv_seg_len;
-            kc = vc = jj * LK - seg * p.kv_seg_len;
+            const int seg = (j * BN) / p.kv_seg_len;
+            kc = vc = j * BN - seg * p.kv_seg_len;
             kb = seg * p.B + b;
           }
           mbar_wait_wd(kv_empty + s, ph ^ 1);
-          mbar_expect_tx(kv_full + s, K_BYTES + V_BYTES);
-          tma_load_4d(sK + s * K_BYTES, &tmK, kv_full + s, 0, kc, hk, kb);
-          if constexpr (kPV16) {   // byte coordinates: 2 bytes per key
-            tma_load_4d(sV + s * V_BYTES, &tmV, kv_full + s, vc * 2, 0, hk, kb);
-            tma_load_4d(sV + s * V_BYTES + VT_BYTES, &tmV, kv_full + s, (vc + BN) * 2, 0, hk, kb);
-          } else {
-            tma_load_4d(sV + s * V_BYTES, &tmV, kv_full + s, vc, 0, hk, kb);
-          }
+          mbar_expect_tx(kv_full + s, K_TILE + V_TILE);
+          tma_load_4d(sK + s * K_TILE, &tmK, kv_full + s, 0, kc, hk, kb);
+          tma_load_4d(sV + s * V_TILE, &tmV, kv_full + s, vc * (kPV16 ? 2 : 1), 0, hk, kb);   // byte coordinate
         }
       }
     } else if (warp == 9) {
@@ -144,10 +138,14 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint64_t dQ = make_smem_desc<SWQK>(smem_u32(sQ));
         const uint64_t dK0 = make_smem_desc<SWQK>(smem_u32(sK));
-        const uint64_t dV0 = make_smem_desc<128>(smem_u32(sV));
-        auto issue_qk = [&](int t) {
-          const int st = (t >> 1) % NS;
-          const uint64_t dK = dK0 + uint64_t(st) * (K_BYTES >> 4) + uint64_t(t & 1) * K_HALF;
+        const uint64_t dV0 = make_smem_desc<SWV>(smem_u32(sV));
+        auto issue_qk = [&](int t, bool wait_kv) {
+          const int st = t % NS;
+          if (wait_kv) {
+            mbar_wait_wd(kv_full + st, (t / NS) & 1);    // K(t) (and V^T(t)) landed
+            tc_fence_after();
+          }
+          const uint64_t dK = dK0 + uint64_t(st) * (K_TILE >> 4);
           const uint32_t tS = tmem_u + (t & 1) * BN;
           if (elect_one()) {
 #pragma unroll
@@ -155,12 +153,10 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         };
         mbar_wait_wd(q_full, 0);
-        mbar_wait_wd(kv_full + 0, 0);
-        tc_fence_after();
-        issue_qk(0);
+        issue_qk(0, true);
         if (elect_one()) tc_commit(s_full + 0);
         if (n_kv > 1) {
-          issue_qk(1);
+          issue_qk(1, true);
           if (elect_one()) tc_commit(s_full + 1);
         }
 #ifdef SAB_TIMELINE
@@ -169,27 +165,26 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #endif
         for (int j = 0; j < n_kv; ++j) {
           SAB_TL(8);
-          // operands of this step that come from a NEW stage: wait for them while P(j) is still being produced
-          if ((j & 1) == 0 && j + 2 < n_kv) mbar_wait_wd(kv_full + ((j + 2) >> 1) % NS, (((j + 2) >> 1) / NS) & 1);
+          // K(j+2) comes from a slot filled several tiles ago: check it while P(j) is still being produced
+          if (j + 2 < n_kv) mbar_wait_wd(kv_full + (j + 2) % NS, ((j + 2) / NS) & 1);
           mbar_wait_wd(p_full + (j & 1), (j >> 1) & 1);   // P(j) stored + O rescaled (also: S(j) fully consumed)
           tc_fence_after();
           SAB_TL(9);
-          const int st = (j >> 1) % NS;
-          const uint64_t dV = dV0 + uint64_t(st) * (V_BYTES >> 4) + uint64_t(j & 1) * V_HALF;
+          const int st = j % NS;
+          const uint64_t dV = dV0 + uint64_t(st) * (V_TILE >> 4);
           const uint32_t tP = tmem_u + (j & 1) * BN;
           if (elect_one()) {
 #pragma unroll
-            if constexpr (kPV16) {
-              for (int k = 0; k < BN / 16; ++k) umma_f16_ts(tmem_u + 128, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
-            } else {
-              for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tmem_u + 128, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
+            for (int k = 0; k < (kPV16 ? BN / 16 : BN / 32); ++k) {
+              if constexpr (kPV16) umma_f16_ts(tmem_u + 128, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
+              else umma_f8_ts(tmem_u + 128, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
             }
           }
           SAB_TL(10);
-          if (j + 2 < n_kv) issue_qk(j + 2);               // reuses S buffer j&1 (after PV(j): in-order pipe)
+          if (j + 2 < n_kv) issue_qk(j + 2, false);        // reuses S buffer j&1 (after PV(j): in-order pipe)
           if (elect_one()) {
             tc_commit(s_full + (j & 1));
-            if ((j & 1) == 1 || j == n_kv - 1) tc_commit(kv_empty + st);   // stage fully consumed once this step retires
+            tc_commit(kv_empty + st);                      // slot j consumed once this step retires
           }
           SAB_TL(11);
         }
@@ -202,9 +197,7 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t lane_off = static_cast<uint32_t>((warp - 4) * 32) << 16;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait_wd(a_full + (j & 1), (j >> 1) & 1);
-      tc_fence_after();
-      const float alpha = __uint_as_float(tmem_ld1(tmem_base + lane_off + (j & 1) * BN + kAlphaCol));
-      tc_wait_ld();
+      const float alpha = s_alpha[(j & 1) * BM + row];
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
         mbar_wait_wd(s_full + ((j + 1) & 1), s_parity(j + 1));   // step(j-1) retired: PV(j-1) is in O
         tc_fence_after();
@@ -316,11 +309,9 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const float alpha = ex2_approx(m - m_new);
         d *= alpha;
         m = m_new;
-        // publish alpha through a dead column of this S buffer (shared memory is full: two CTAs per SM): the correction
-        // warpgroup rescales this row of O (in TMEM) concurrently with the exponentials below
-        tmem_st1(tS + kAlphaCol, __float_as_uint(alpha));
-        tc_wait_st();
-        tc_fence_before();
+        // publish alpha: the correction warpgroup rescales this row of O (in TMEM) concurrently with the exponentials.
+        // Double-buffered: alpha(j+2) is written only after s_full(j+2), i.e. after the correction warp read alpha(j).
+        s_alpha[(j & 1) * BM + row] = alpha;
         mbar_arrive(a_full + (j & 1));
         const float nm = -m_new;
         SAB_TL(3);
@@ -512,9 +503,9 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     dim3 g2((grid.x + 1) / 2, grid.y, grid.z);
     return launch_attn_pair<D, kKT, OutT>(tq, tk, tv, p, g2, stream);
   }
-  constexpr int NS = kPV16 ? ((D == 128) ? 2 : 4) : ((D == 128) ? 3 : 6);
-  // Q tile + NS x (K + V^T stage) + barriers = 112.1 KB -> exactly two CTAs (2 x 256 TMEM columns) fit the 228 KB of an SM
-  size_t smem = size_t(BM) * D + size_t(NS) * (LK * D + LK * D * (kPV16 ? 2 : 1)) + 256;
+  constexpr int NS = kPV16 ? ((D == 128) ? 3 : 6) : ((D == 128) ? 5 : 10);
+  // Q tile + NS x (K + V^T 64-key tile) + alpha hand-off + barriers (97.5 KB at hd128): two CTAs per SM (TMEM: 2 x 256 columns)
+  size_t smem = size_t(BM) * D + size_t(NS) * (BN * D + BN * D * (kPV16 ? 2 : 1)) + 2 * BM * sizeof(float) + 512;
   if (smem < 80 * 1024) smem = 80 * 1024;
   auto kern = sage_attn_fwd_kernel<D, kKT, OutT, kPV16>;
   static bool configured = false;
@@ -562,20 +553,25 @@ static int attn_entry(int pv16, const int8_t* q_int8, const int8_t* k_int8, cons
 
   CUtensorMap tq, tk, tv;
   const int swqk = D == 128 ? 128 : 64;
+  // box sizes: the single-tile kernel streams 64-key tiles, the paired-tile experiment 128-key stages
+  const bool pairk = !pv16 && use_pair_kernel();
+  const uint32_t kbox = pairk ? LK : BN;
+  const uint32_t vbox = pairk ? LK : (pv16 ? 128 : BN);   // bytes of one V^T row in the box
+  const int swv = pairk ? 128 : (pv16 ? 128 : 64);
   if (kv_seg_len > 0) {
     const int P = Skv / kv_seg_len;
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, B, q_stride_s, q_stride_h, q_stride_b, D, BM, swqk))) return st;
-    if ((st = make_map_u8(&tk, k_int8, D, kv_seg_len, Hkv, uint64_t(B) * P, k_stride_s, k_stride_h, k_stride_b, D, LK, swqk))) return st;
-    if ((st = make_map_u8(&tv, v_fp8, v_s_pad * vb, D, Hkv, uint64_t(B) * P, v_s_pad * vb, uint64_t(v_s_pad) * D * vb, uint64_t(v_s_pad) * D * Hkv * vb, LK, D, 128))) return st;
+    if ((st = make_map_u8(&tk, k_int8, D, kv_seg_len, Hkv, uint64_t(B) * P, k_stride_s, k_stride_h, k_stride_b, D, kbox, swqk))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad * vb, D, Hkv, uint64_t(B) * P, v_s_pad * vb, uint64_t(v_s_pad) * D * vb, uint64_t(v_s_pad) * D * Hkv * vb, vbox, D, swv))) return st;
   } else if (!varlen) {
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, B, q_stride_s, q_stride_h, q_stride_b, D, BM, swqk))) return st;
-    if ((st = make_map_u8(&tk, k_int8, D, Skv > 0 ? Skv : 1, Hkv, B, k_stride_s, k_stride_h, k_stride_b, D, LK, swqk))) return st;
-    if ((st = make_map_u8(&tv, v_fp8, v_s_pad * vb, D, Hkv, B, v_s_pad * vb, uint64_t(v_s_pad) * D * vb, uint64_t(v_s_pad) * D * Hkv * vb, LK, D, 128))) return st;
+    if ((st = make_map_u8(&tk, k_int8, D, Skv > 0 ? Skv : 1, Hkv, B, k_stride_s, k_stride_h, k_stride_b, D, kbox, swqk))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad * vb, D, Hkv, B, v_s_pad * vb, uint64_t(v_s_pad) * D * vb, uint64_t(v_s_pad) * D * Hkv * vb, vbox, D, swv))) return st;
   } else {
     // packed [T,H,D]: Sq / Skv are the TOTAL token counts
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, 1, q_stride_s, q_stride_h, 0, D, BM, swqk))) return st;
-    if ((st = make_map_u8(&tk, k_int8, D, Skv, Hkv, 1, k_stride_s, k_stride_h, 0, D, LK, swqk))) return st;
-    if ((st = make_map_u8(&tv, v_fp8, v_s_pad * vb, D, Hkv, 1, v_s_pad * vb, uint64_t(v_s_pad) * D * vb, 0, LK, D, 128))) return st;
+    if ((st = make_map_u8(&tk, k_int8, D, Skv, Hkv, 1, k_stride_s, k_stride_h, 0, D, kbox, swqk))) return st;
+    if ((st = make_map_u8(&tv, v_fp8, v_s_pad * vb, D, Hkv, 1, v_s_pad * vb, uint64_t(v_s_pad) * D * vb, 0, vbox, D, swv))) return st;
   }
 
   AttnParams p{};
