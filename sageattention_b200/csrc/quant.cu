@@ -31,6 +31,29 @@ __device__ __forceinline__ void load8(const T* p, float (&f)[8]) {
   for (int i = 0; i < 8; ++i) f[i] = to_f<T>(e[i]);
 }
 
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fmul2q(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2q(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t ffma2q(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 __device__ __forceinline__ int8_t cvt_rni_sat_s8(float x) {  // csrc/numeric_conversion.cuh:144-148
   int r;
   asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -131,7 +154,7 @@ struct QuantParams {
 };
 
 template <typename T, int D, int MODE>
-__global__ void __launch_bounds__(256) quant_int8_kernel(const QuantParams p) {
+__global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p) {
   constexpr int TPR = D / 8;
   constexpr int RPP = 256 / TPR;     // 16 (D=128) / 32 (D=64)
   constexpr int NP = 128 / RPP;      // passes: 8 / 4
@@ -164,31 +187,34 @@ __global__ void __launch_bounds__(256) quant_int8_kernel(const QuantParams p) {
   __shared__ float s_scale[32];
   __shared__ float s_inv[32];   // RN(1/scale): fast path of the Triton-semantics division
 
-  float v[NP][8];
+  // The tile stays in registers as raw 16-bit data (NP x 16 B) and is converted twice (amax pass, quantise pass):
+  // half the registers of an fp32 copy -> four CTAs per SM, which is what hides the DRAM latency of this
+  // load -> reduce -> sync -> store kernel.
+  auto xform = [&](T e, int i) -> float {
+    float f = to_f<T>(e);
+    if (p.mean != nullptr) {
+      f -= mean[i];
+      if (p.semantics == SAB_SEM_TRITON) f = to_f<T>(from_f<T>(f));   // `k - km` rounds to the input dtype
+    }
+    if (p.has_sm_scale) f *= p.sm_scale;
+    return f;
+  };
+  uint4 raw[NP];
+#pragma unroll
+  for (int ps = 0; ps < NP; ++ps) {
+    const int row = tile * 128 + ps * RPP + tr;
+    raw[ps] = make_uint4(0, 0, 0, 0);
+    if (row < S) raw[ps] = *reinterpret_cast<const uint4*>(xb + int64_t(row) * p.xss);
+  }
 #pragma unroll
   for (int ps = 0; ps < NP; ++ps) {
     const int r = ps * RPP + tr;
     const int row = tile * 128 + r;
     float amax = 0.f;
     if (row < S) {
-      load8<T>(xb + int64_t(row) * p.xss, v[ps]);
-      if (p.mean != nullptr) {
+      const T* e = reinterpret_cast<const T*>(&raw[ps]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float t = v[ps][i] - mean[i];
-          if (p.semantics == SAB_SEM_TRITON) t = to_f<T>(from_f<T>(t));  // `k - km` rounds to the input dtype
-          v[ps][i] = t;
-        }
-      }
-      if (p.has_sm_scale) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[ps][i] *= p.sm_scale;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[ps][i]));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[ps][i] = 0.f;
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(xform(e[i], i)));
     }
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -225,7 +251,7 @@ __global__ void __launch_bounds__(256) quant_int8_kernel(const QuantParams p) {
       mult = scale;
     }
     s_scale[g] = mult;
-    s_inv[g] = __fdiv_rn(1.0f, mult);
+    s_inv[g] = mult > 0.f ? __fdiv_rn(1.0f, mult) : 0.f;   // all-zero block (scale 0): reference 0/0 -> NaN -> int8 0
     const int gcol = tile * ngroups + g;
     if (varlen) {
       const int nblk = (S + p.blk - 1) / p.blk;
@@ -247,26 +273,48 @@ __global__ void __launch_bounds__(256) quant_int8_kernel(const QuantParams p) {
     else if (MODE == kGroupThreadQ) g = (r / 32) * 8 + (r % 8);
     else g = (r / 64) * 4 + (r % 8) / 2;
     const float mult = s_scale[g];
+    const T* e = reinterpret_cast<const T*>(&raw[ps]);
     int8_t q[8];
     if (p.semantics == SAB_SEM_CUDA) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = cvt_rni_sat_s8(v[ps][i] * mult);
+      for (int i = 0; i < 8; ++i) q[i] = cvt_rni_sat_s8(xform(e[i], i) * mult);
     } else {
       // x / scale must be the correctly-rounded IEEE quotient to stay bit-exact with the reference (Triton `x / scale`).
       // Fast path: x * RN(1/scale) differs from it by < 2.4e-5 at |y| <= 127.5, so after adding the +-0.5 rounding
       // offset the truncation can only differ when z lies within 1e-4 of an integer; only those (rare, ~2e-4)
       // elements take the exact division.  Removes the per-element MUFU.RCP + Newton sequence (4x kernel time).
+      // Two elements per instruction (FMUL2 / FADD2 / FFMA2): z = y + copysign(0.5, y); its distance to the nearest
+      // integer (1.5*2^23 magic constant, exact) decides fast path vs exact division; F2I.TRUNC is the only XU op.
       const float inv = s_inv[g];
+      const uint64_t inv2 = pack2f(inv, inv);
+      const uint64_t magic2 = pack2f(12582912.0f, 12582912.0f);
+      const uint64_t nmagic2 = pack2f(-12582912.0f, -12582912.0f);
+      const uint64_t mone2 = pack2f(-1.0f, -1.0f);
+      float zz[8];
+      bool slow = false;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float y = v[ps][i] * inv;
-        float z = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);     // quant_per_block.py:43-45
-        if (fabsf(z - rintf(z)) < 1e-4f) {
-          y = __fdiv_rn(v[ps][i], mult);
-          z = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
-        }
-        q[i] = static_cast<int8_t>(static_cast<int>(z));     // truncation toward zero
+      for (int i = 0; i < 8; i += 2) {
+        const float x0 = xform(e[i], i), x1 = xform(e[i + 1], i + 1);
+        float y0, y1;
+        unpack2f(fmul2q(pack2f(x0, x1), inv2), y0, y1);
+        const float h0 = __uint_as_float(0x3F000000u | (__float_as_uint(y0) & 0x80000000u));   // quant_per_block.py:43-45
+        const float h1 = __uint_as_float(0x3F000000u | (__float_as_uint(y1) & 0x80000000u));
+        const uint64_t z2 = fadd2q(pack2f(y0, y1), pack2f(h0, h1));
+        const uint64_t n2 = fadd2q(fadd2q(z2, magic2), nmagic2);        // nearest integer to z (exact)
+        float d0, d1;
+        unpack2f(z2, zz[i], zz[i + 1]);
+        unpack2f(ffma2q(n2, mone2, z2), d0, d1);                         // z - n, exact
+        slow |= (fminf(fabsf(d0), fabsf(d1)) < 1e-4f);
       }
+      if (slow) {   // rare (~1e-3 of the rows): the rounding of a quotient could change trunc(z) -> exact IEEE division
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y = __fdiv_rn(xform(e[i], i), mult);
+          zz[i] = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = static_cast<int8_t>(__float2int_rz(zz[i]));
     }
     *reinterpret_cast<uint2*>(ob + int64_t(row) * p.oss) = *reinterpret_cast<uint2*>(q);
   }
