@@ -484,17 +484,36 @@ template <int D, bool kKT, typename OutT>
 int launch_attn_pair(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                      cudaStream_t stream);
 
-// SAB_ATTN_KERNEL=single|pair selects the kernel.  Default: single (one Q tile per CTA, two CTAs per SM) — measured
-// faster on B200 (1.28 vs 1.06 PFLOP/s at hd128 S=8192); pair (attn_pair.cu: two Q tiles per CTA, exp ping-pong) is kept
-// as an experiment: with one warp per scheduler in the exp phase it is latency-bound (see DESIGN.md §4.1).
-static bool use_pair_kernel() {
+// attn_hd64.cu: head_dim 64, four CTAs per SM (S single-buffered).  SAB_HD64_KERNEL=2cta falls back to the generic kernel.
+template <bool kKT, typename OutT>
+int launch_attn_hd64(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                     cudaStream_t stream);
+static bool use_hd64_kernel() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("SAB_ATTN_KERNEL");
-    v = (e != nullptr && e[0] == 'p') ? 1 : 0;
+    const char* e = getenv("SAB_HD64_KERNEL");
+    v = (e != nullptr && e[0] == '2') ? 0 : 1;
   }
   return v == 1;
 }
+
+// SAB_ATTN_KERNEL=single|pair selects the kernel.  Default: single (one Q tile per CTA, two CTAs per SM) — measured
+// faster on B200 (1.28 vs 1.06 PFLOP/s at hd128 S=8192); pair (attn_pair.cu: two Q tiles per CTA, exp ping-pong) is kept
+// as an experiment: with one warp per scheduler in the exp phase it is latency-bound (see DESIGN.md §4.1).
+static int attn_kernel_mode() {   // 0 single, 1 pair, 2 split (attn_split.cu: two softmax threads per row)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAB_ATTN_KERNEL");
+    v = (e == nullptr) ? 0 : (e[0] == 'p' ? 1 : (e[0] == 's' && e[1] == 'p' ? 2 : 0));
+  }
+  return v;
+}
+static bool use_pair_kernel() { return attn_kernel_mode() == 1; }
+
+// attn_split.cu
+template <int D, bool kKT, typename OutT>
+int launch_attn_split(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                      cudaStream_t stream);
 
 template <int D, bool kKT, typename OutT, bool kPV16>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
@@ -502,6 +521,12 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   if (!kPV16 && use_pair_kernel()) {
     dim3 g2((grid.x + 1) / 2, grid.y, grid.z);
     return launch_attn_pair<D, kKT, OutT>(tq, tk, tv, p, g2, stream);
+  }
+  if constexpr (!kPV16) {
+    if (attn_kernel_mode() == 2 && p.dbg == nullptr) return launch_attn_split<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
+  }
+  if constexpr (D == 64 && !kPV16) {
+    if (use_hd64_kernel() && p.dbg == nullptr) return launch_attn_hd64<kKT, OutT>(tq, tk, tv, p, grid, stream);
   }
   constexpr int NS = kPV16 ? ((D == 128) ? 3 : 6) : ((D == 128) ? 5 : 10);
   // Q tile + NS x (K + V^T 64-key tile) + alpha hand-off + barriers (97.5 KB at hd128): two CTAs per SM (TMEM: 2 x 256 columns)
