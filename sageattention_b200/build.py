@@ -1,6 +1,6 @@
 """Build the sm_100a CUDA library in-tree: sageattention_b200/lib/libsageattn_b200.so.
 
-One nvcc invocation, no torch headers (the boundary is a plain C ABI, include/sageattn_b200.h).
+One nvcc compile per source (in parallel) + one link, no torch headers (the boundary is a plain C ABI, include/sageattn_b200.h).
 nvcc cross-compiles without a GPU; the .so travels to the GPU box with the repo snapshot.
 """
 import os, subprocess, sys, hashlib
@@ -11,7 +11,9 @@ LIB = os.path.join(HERE, "lib", "libsageattn_b200.so")
 SOURCES = ["attn.cu", "attn_pair.cu", "attn_hd64.cu", "attn_split.cu", "quant.cu", "capi.cu"]
 HEADERS = ["ptx.cuh", "common.cuh", "attn_common.cuh", os.path.join("..", "..", "include", "sageattn_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# per-source extra nvcc flags (none at present)
+EXTRA_FLAGS = {}
 
 
 def _digest():
@@ -19,7 +21,7 @@ def _digest():
     for f in SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + repr(sorted(EXTRA_FLAGS.items()))).encode())
     return h.hexdigest()
 
 
@@ -30,14 +32,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libsageattn_b200.so")
+    objdir = os.path.join(os.path.dirname(LIB), "obj")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        return src, obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    log = "".join(f"==== {src}\n{r.stdout}{r.stderr}" for src, _, r in results)
+    failed = [src for src, _, r in results if r.returncode != 0]
+    link = None
+    if not failed:
+        link = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB] +
+                              [obj for _, obj, _ in results], capture_output=True, text=True)
+        log += link.stdout + link.stderr
+    if verbose or failed or (link is not None and link.returncode != 0):
+        sys.stderr.write(log)
+    if failed or link.returncode != 0:
+        raise RuntimeError("nvcc failed building libsageattn_b200.so (%s)" % (", ".join(failed) or "link"))
     with open(os.path.join(os.path.dirname(LIB), "ptxas.log"), "w") as fh:
-        fh.write(res.stdout + res.stderr)
+        fh.write(log)
     with open(stamp, "w") as fh:
         fh.write(dig)
     return LIB

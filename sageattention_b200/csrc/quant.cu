@@ -153,8 +153,49 @@ struct QuantParams {
   const int32_t* cu; const int32_t* cu_scale;
 };
 
-template <typename T, int D, int MODE>
+// Two 16-bit elements of one 32-bit word -> two floats (exact).
+template <typename T>
+__device__ __forceinline__ void cvt_pair(uint32_t w, float& lo, float& hi);
+template <>
+__device__ __forceinline__ void cvt_pair<__nv_bfloat16>(uint32_t w, float& lo, float& hi) {
+  lo = __uint_as_float(w << 16);
+  hi = __uint_as_float(w & 0xffff0000u);
+}
+template <>
+__device__ __forceinline__ void cvt_pair<__half>(uint32_t w, float& lo, float& hi) {
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+  lo = f.x;
+  hi = f.y;
+}
+// Two floats -> one word of two T (round to nearest even).
+template <typename T>
+__device__ __forceinline__ uint32_t round_pair(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t round_pair<__nv_bfloat16>(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t round_pair<__half>(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+constexpr int kQfTriton = 1, kQfMean = 2, kQfSmScale = 4;   // FLAGS bits of quant_int8_kernel
+
+// FLAGS (compile time): rounding semantics, fused mean subtraction, fused sm_scale multiply — no per-element
+// runtime conditionals.  The tile stays in registers as raw 16-bit words (NP x 16 B per thread).
+//   amax pass : |x| after the transform; the sm_scale multiply is applied once to the ROW maximum, which is exact:
+//               rounding and multiplication by a positive constant are monotone, so max_i RN(|x_i| s) = RN(max_i |x_i| s).
+//   int8 pass : y = x * (1/scale or 127/amax); t = y + 1.5*2^23 rounds y to the nearest-even integer n, and the low
+//               byte of t's bit pattern IS the two's-complement int8 — no F2I, bytes gathered with PRMT.
+//               CUDA semantics (cvt.rni.sat.s8 of x*mult, |y| <= 127 by construction): that is already the result.
+//               Triton semantics need trunc(RN(x/scale) + 0.5 sign): equal to n unless y is within 1e-4 of a
+//               half-integer (ties, or the 2.4e-5 error of x*RN(1/scale) against the IEEE quotient could matter);
+//               one |y - n| maximum per 8 elements decides, and those rare rows redo the exact reference sequence.
+template <typename T, int D, int MODE, int FLAGS>
 __global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p) {
+  constexpr bool kTriton = (FLAGS & kQfTriton) != 0, kMean = (FLAGS & kQfMean) != 0, kSms = (FLAGS & kQfSmScale) != 0;
   constexpr int TPR = D / 8;
   constexpr int RPP = 256 / TPR;     // 16 (D=128) / 32 (D=64)
   constexpr int NP = 128 / RPP;      // passes: 8 / 4
@@ -178,27 +219,18 @@ __global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p)
   const T* xb = reinterpret_cast<const T*>(p.x) + x_off + tc * 8;
   int8_t* ob = p.out + o_off + tc * 8;
 
-  float mean[8];
-  if (p.mean != nullptr) {
+  uint64_t nmean2[4];   // (-mean[2w], -mean[2w+1])
+  if constexpr (kMean) {
+    float mean[8];
     load8<T>(reinterpret_cast<const T*>(p.mean) + (int64_t(varlen ? 0 : b) * p.H + h) * D + tc * 8, mean);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) nmean2[w] = pack2f(-mean[2 * w], -mean[2 * w + 1]);
   }
 
   __shared__ float s_row_amax[128];
   __shared__ float s_scale[32];
   __shared__ float s_inv[32];   // RN(1/scale): fast path of the Triton-semantics division
 
-  // The tile stays in registers as raw 16-bit data (NP x 16 B) and is converted twice (amax pass, quantise pass):
-  // half the registers of an fp32 copy -> four CTAs per SM, which is what hides the DRAM latency of this
-  // load -> reduce -> sync -> store kernel.
-  auto xform = [&](T e, int i) -> float {
-    float f = to_f<T>(e);
-    if (p.mean != nullptr) {
-      f -= mean[i];
-      if (p.semantics == SAB_SEM_TRITON) f = to_f<T>(from_f<T>(f));   // `k - km` rounds to the input dtype
-    }
-    if (p.has_sm_scale) f *= p.sm_scale;
-    return f;
-  };
   uint4 raw[NP];
 #pragma unroll
   for (int ps = 0; ps < NP; ++ps) {
@@ -206,16 +238,36 @@ __global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p)
     raw[ps] = make_uint4(0, 0, 0, 0);
     if (row < S) raw[ps] = *reinterpret_cast<const uint4*>(xb + int64_t(row) * p.xss);
   }
+  // transform of one word before the sm_scale multiply: x - mean (Triton: `k - km` rounds to the input dtype)
+  auto centred = [&](uint32_t w, int wi, float& lo, float& hi) {
+    cvt_pair<T>(w, lo, hi);
+    if constexpr (kMean) {
+      unpack2f(fadd2q(pack2f(lo, hi), nmean2[wi]), lo, hi);
+      if constexpr (kTriton) cvt_pair<T>(round_pair<T>(lo, hi), lo, hi);
+    }
+  };
 #pragma unroll
   for (int ps = 0; ps < NP; ++ps) {
     const int r = ps * RPP + tr;
     const int row = tile * 128 + r;
     float amax = 0.f;
-    if (row < S) {
-      const T* e = reinterpret_cast<const T*>(&raw[ps]);
+    uint32_t* wv = reinterpret_cast<uint32_t*>(&raw[ps]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(xform(e[i], i)));
+    for (int w = 0; w < 4; ++w) {
+      float lo, hi;
+      if constexpr (kMean && kTriton) {
+        // the centred value is a T again: keep it in place of the input so the int8 pass does not redo the subtraction
+        cvt_pair<T>(wv[w], lo, hi);
+        unpack2f(fadd2q(pack2f(lo, hi), nmean2[w]), lo, hi);
+        wv[w] = round_pair<T>(lo, hi);
+        cvt_pair<T>(wv[w], lo, hi);
+      } else {
+        centred(wv[w], w, lo, hi);
+      }
+      amax = fmaxf(fmaxf(amax, fabsf(lo)), fabsf(hi));
     }
+    if (row >= S) amax = 0.f;   // (rows past the end were loaded as zeros; with a mean they would read |0 - mean|)
+    if constexpr (kSms) amax *= p.sm_scale;
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if (tc == 0) s_row_amax[r] = amax;
@@ -241,7 +293,7 @@ __global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p)
       }
     }
     float scale, mult;
-    if (p.semantics == SAB_SEM_CUDA) {   // fused.cu:147-184 (compiled with --use_fast_math there)
+    if constexpr (!kTriton) {   // fused.cu:147-184 (compiled with --use_fast_math there)
       amax = fmaxf(amax, 0.0000001f);
       scale = __fdividef(amax, 127.0f);
       mult = __fdividef(127.0f, amax);
@@ -263,6 +315,10 @@ __global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p)
   __syncthreads();
 
   // ---- quantise + store
+  const uint64_t magic2 = pack2f(12582912.0f, 12582912.0f);
+  const uint64_t nmagic2 = pack2f(-12582912.0f, -12582912.0f);
+  const uint64_t mone2 = pack2f(-1.0f, -1.0f);
+  const uint64_t sms2 = pack2f(p.sm_scale, p.sm_scale);
 #pragma unroll
   for (int ps = 0; ps < NP; ++ps) {
     const int r = ps * RPP + tr;
@@ -273,50 +329,75 @@ __global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p)
     else if (MODE == kGroupThreadQ) g = (r / 32) * 8 + (r % 8);
     else g = (r / 64) * 4 + (r % 8) / 2;
     const float mult = s_scale[g];
-    const T* e = reinterpret_cast<const T*>(&raw[ps]);
-    int8_t q[8];
-    if (p.semantics == SAB_SEM_CUDA) {
+    const float fac = kTriton ? s_inv[g] : mult;
+    const uint64_t fac2 = pack2f(fac, fac);
+    const uint32_t* wv = reinterpret_cast<const uint32_t*>(&raw[ps]);
+    uint32_t tb[8];     // bit patterns of y + 1.5*2^23: low byte = int8
+    float dmax = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = cvt_rni_sat_s8(xform(e[i], i) * mult);
-    } else {
-      // x / scale must be the correctly-rounded IEEE quotient to stay bit-exact with the reference (Triton `x / scale`).
-      // Fast path: x * RN(1/scale) differs from it by < 2.4e-5 at |y| <= 127.5, so after adding the +-0.5 rounding
-      // offset the truncation can only differ when z lies within 1e-4 of an integer; only those (rare, ~2e-4)
-      // elements take the exact division.  Removes the per-element MUFU.RCP + Newton sequence (4x kernel time).
-      // Two elements per instruction (FMUL2 / FADD2 / FFMA2): z = y + copysign(0.5, y); its distance to the nearest
-      // integer (1.5*2^23 magic constant, exact) decides fast path vs exact division; F2I.TRUNC is the only XU op.
-      const float inv = s_inv[g];
-      const uint64_t inv2 = pack2f(inv, inv);
-      const uint64_t magic2 = pack2f(12582912.0f, 12582912.0f);
-      const uint64_t nmagic2 = pack2f(-12582912.0f, -12582912.0f);
-      const uint64_t mone2 = pack2f(-1.0f, -1.0f);
-      float zz[8];
-      bool slow = false;
-#pragma unroll
-      for (int i = 0; i < 8; i += 2) {
-        const float x0 = xform(e[i], i), x1 = xform(e[i + 1], i + 1);
-        float y0, y1;
-        unpack2f(fmul2q(pack2f(x0, x1), inv2), y0, y1);
-        const float h0 = __uint_as_float(0x3F000000u | (__float_as_uint(y0) & 0x80000000u));   // quant_per_block.py:43-45
-        const float h1 = __uint_as_float(0x3F000000u | (__float_as_uint(y1) & 0x80000000u));
-        const uint64_t z2 = fadd2q(pack2f(y0, y1), pack2f(h0, h1));
-        const uint64_t n2 = fadd2q(fadd2q(z2, magic2), nmagic2);        // nearest integer to z (exact)
+    for (int w = 0; w < 4; ++w) {
+      float lo, hi;
+      if constexpr (kMean && kTriton) cvt_pair<T>(wv[w], lo, hi);   // already centred and rounded in place
+      else centred(wv[w], w, lo, hi);
+      uint64_t x2 = pack2f(lo, hi);
+      if constexpr (kSms) x2 = fmul2q(x2, sms2);
+      // y must be rounded on its own (the reference rounds x*mult, then converts): ptxas contracts `mul.rn.f32x2` +
+      // `add.rn.f32x2` into one FFMA2 (even with --fmad=false) when y has no other consumer, and the single rounding
+      // flips x.5 ties (63 vs 64).  Both semantics therefore consume y a second time (Triton: y - n; CUDA: the
+      // saturation guard below), which keeps the two instructions apart — checked in SASS (FADD2 count) at build time.
+      const uint64_t y2 = fmul2q(x2, fac2);
+      const uint64_t t2 = fadd2q(y2, magic2);
+      if constexpr (kTriton) {
         float d0, d1;
-        unpack2f(z2, zz[i], zz[i + 1]);
-        unpack2f(ffma2q(n2, mone2, z2), d0, d1);                         // z - n, exact
-        slow |= (fminf(fabsf(d0), fabsf(d1)) < 1e-4f);
+        unpack2f(ffma2q(fadd2q(t2, nmagic2), mone2, y2), d0, d1);   // y - n, exact
+        dmax = fmaxf(fmaxf(dmax, fabsf(d0)), fabsf(d1));
+      } else {
+        float y0, y1;
+        unpack2f(y2, y0, y1);
+        dmax = fmaxf(fmaxf(dmax, fabsf(y0)), fabsf(y1));   // cvt.rni.sat.s8 saturates; the byte trick wraps
       }
-      if (slow) {   // rare (~1e-3 of the rows): the rounding of a quotient could change trunc(z) -> exact IEEE division
+      float t0, t1;
+      unpack2f(t2, t0, t1);
+      tb[2 * w] = __float_as_uint(t0);
+      tb[2 * w + 1] = __float_as_uint(t1);
+    }
+    if constexpr (!kTriton) {
+      if (dmax > 127.49f) {   // never for finite data (|x| <= amax by construction): saturate like cvt.rni.sat.s8
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float y = __fdiv_rn(xform(e[i], i), mult);
-          zz[i] = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);
+        for (int w = 0; w < 4; ++w) {
+          float xs[2];
+          centred(wv[w], w, xs[0], xs[1]);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float x = xs[i];
+            if constexpr (kSms) x = __fmul_rn(x, p.sm_scale);
+            tb[2 * w + i] = uint32_t(int(cvt_rni_sat_s8(__fmul_rn(x, mult))));
+          }
         }
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = static_cast<int8_t>(__float2int_rz(zz[i]));
     }
-    *reinterpret_cast<uint2*>(ob + int64_t(row) * p.oss) = *reinterpret_cast<uint2*>(q);
+    if constexpr (kTriton) {
+      if (dmax > 0.4999f) {   // rare (~1e-3 of the rows): redo the reference sequence with the exact IEEE quotient
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          float xs[2];
+          if constexpr (kMean) cvt_pair<T>(wv[w], xs[0], xs[1]);
+          else centred(wv[w], w, xs[0], xs[1]);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float x = xs[i];
+            if constexpr (kSms) x = __fmul_rn(x, p.sm_scale);
+            const float y = __fdiv_rn(x, mult);
+            const float z = __fadd_rn(y, y >= 0.f ? 0.5f : -0.5f);   // quant_per_block.py:43-45
+            tb[2 * w + i] = uint32_t(__float2int_rz(z));              // NaN (0/0, all-zero block) -> 0
+          }
+        }
+      }
+    }
+    uint2 q;
+    q.x = __byte_perm(__byte_perm(tb[0], tb[1], 0x0040), __byte_perm(tb[2], tb[3], 0x0040), 0x5410);
+    q.y = __byte_perm(__byte_perm(tb[4], tb[5], 0x0040), __byte_perm(tb[6], tb[7], 0x0040), 0x5410);
+    *reinterpret_cast<uint2*>(ob + int64_t(row) * p.oss) = q;
   }
 }
 
@@ -441,13 +522,28 @@ static int run_stats(const void* x, int dtype, float* part, int B, int H, int S,
   return D == 128 ? launch_stats<__nv_bfloat16, 128>(x, part, B, H, S, sb, sh, ss, st) : launch_stats<__nv_bfloat16, 64>(x, part, B, H, S, sb, sh, ss, st);
 }
 
-template <typename T, int D>
-static int launch_quant_t(const QuantParams& p, int mode, dim3 grid, cudaStream_t st) {
-  if (mode == kGroupBlock) quant_int8_kernel<T, D, kGroupBlock><<<grid, 256, 0, st>>>(p);
-  else if (mode == kGroupThreadQ) quant_int8_kernel<T, D, kGroupThreadQ><<<grid, 256, 0, st>>>(p);
-  else quant_int8_kernel<T, D, kGroupThreadK><<<grid, 256, 0, st>>>(p);
+template <typename T, int D, int FLAGS>
+static int launch_quant_f(const QuantParams& p, int mode, dim3 grid, cudaStream_t st) {
+  if (mode == kGroupBlock) quant_int8_kernel<T, D, kGroupBlock, FLAGS><<<grid, 256, 0, st>>>(p);
+  else if (mode == kGroupThreadQ) quant_int8_kernel<T, D, kGroupThreadQ, FLAGS><<<grid, 256, 0, st>>>(p);
+  else quant_int8_kernel<T, D, kGroupThreadK, FLAGS><<<grid, 256, 0, st>>>(p);
   SAB_CUDA_OK(cudaGetLastError());
   return SAB_OK;
+}
+template <typename T, int D>
+static int launch_quant_t(const QuantParams& p, int mode, dim3 grid, cudaStream_t st) {
+  const int flags = (p.semantics == SAB_SEM_TRITON ? kQfTriton : 0) | (p.mean != nullptr ? kQfMean : 0) |
+                    (p.has_sm_scale ? kQfSmScale : 0);
+  switch (flags) {
+    case 0: return launch_quant_f<T, D, 0>(p, mode, grid, st);
+    case 1: return launch_quant_f<T, D, 1>(p, mode, grid, st);
+    case 2: return launch_quant_f<T, D, 2>(p, mode, grid, st);
+    case 3: return launch_quant_f<T, D, 3>(p, mode, grid, st);
+    case 4: return launch_quant_f<T, D, 4>(p, mode, grid, st);
+    case 5: return launch_quant_f<T, D, 5>(p, mode, grid, st);
+    case 6: return launch_quant_f<T, D, 6>(p, mode, grid, st);
+    default: return launch_quant_f<T, D, 7>(p, mode, grid, st);
+  }
 }
 static int launch_quant(const QuantParams& p, int dtype, int D, int mode, dim3 grid, cudaStream_t st) {
   if (dtype == SAB_DTYPE_FP16) return D == 128 ? launch_quant_t<__half, 128>(p, mode, grid, st) : launch_quant_t<__half, 64>(p, mode, grid, st);
