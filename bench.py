@@ -187,6 +187,7 @@ def run_ours(args):
     value = total_flops / (ms * 1e-3) / 1e12
 
     out = None
+    cached_kv = None
     if world == 1:
         # ---- roofline: the dominant kernel alone (pre-quantised operands), CUDA events on the launch stream
         km = sab.k_mean(k)
@@ -216,10 +217,10 @@ def run_ours(args):
         oh = torch.empty(B, H, S, D, dtype=dtype).pin_memory()
         qd, kd, vd = (torch.empty(B, H, S, D, device=dev, dtype=dtype) for _ in range(3))
 
-        def e2e_step():
-            qd.copy_(qh, non_blocking=True); kd.copy_(kh, non_blocking=True); vd.copy_(vh, non_blocking=True)
-            oo = sab.sageattn(qd, kd, vd, tensor_layout="HND", is_causal=False)
-            oh.copy_(oo, non_blocking=True)
+        del qd, kd, vd
+
+        def e2e_step():   # host-buffer entry point: chunked H2D / sageattn / D2H pipeline (sageattention_b200/host.py)
+            sab.sageattn_host(qh, kh, vh, out=oh, tensor_layout="HND", is_causal=False)
         for _ in range(2):
             e2e_step()
         torch.cuda.synchronize()
@@ -227,7 +228,25 @@ def run_ours(args):
         ems = time_events(e2e_step, esteps)
         nbytes = B * H * S * D * 2
         e2e = {"value": total_flops / (ems * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 3 * nbytes,
-               "d2h_bytes_per_step": nbytes, "ms_per_step": ems}
+               "d2h_bytes_per_step": nbytes, "ms_per_step": ems,
+               "api": "sageattn_host(q, k, v, out): pinned host tensors in, pinned host tensor out, per-(batch, head-group) pipeline"}
+        # the same call without the pipeline (copy in, sageattn, copy out back to back), for reference
+        qd, kd, vd = (torch.empty(B, H, S, D, device=dev, dtype=dtype) for _ in range(3))
+
+        def serial_step():
+            qd.copy_(qh, non_blocking=True); kd.copy_(kh, non_blocking=True); vd.copy_(vh, non_blocking=True)
+            oo = sab.sageattn(qd, kd, vd, tensor_layout="HND", is_causal=False)
+            oh.copy_(oo, non_blocking=True)
+        serial_step()
+        torch.cuda.synchronize()
+        e2e["serial_ms_per_step"] = time_events(serial_step, 3)
+        # K/V quantised once (quantize_kv), each step = Q quantisation + attention (sageattention_b200/cache.py)
+        kvq = sab.quantize_kv(k, v)
+        cached = lambda: sab.sageattn_prequantized(q, kvq)
+        cached()
+        torch.cuda.synchronize()
+        cms = time_events(cached, args.steps)
+        cached_kv = {"value": total_flops / (cms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": cms}
     else:
         roof = {"bound": "tensor", "achieved": value, "peak": 2.0 * pk["bf16_tflops"] * world, "unit": "TFLOP/s",
                 "frac": value / (2.0 * pk["bf16_tflops"] * world), "traffic": None,
@@ -277,7 +296,7 @@ def run_ours(args):
                        "step": "full sageattn(): K-mean + INT8 quant Q/K + FP8 quant V + fused attention"},
             "roofline": roof, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "cpu_baseline": cpu_baseline,
-            "context": {"h100_published_kernel_tops_hd128_8k_noncausal": 900,
+            "context": {"h100_published_kernel_tops_hd128_8k_noncausal": 900, "cached_kv": cached_kv,
                         "note": "reference publishes kernel-only numbers on other hardware (BASELINE.md); no B200 number exists"},
         }
         print(json.dumps(line))

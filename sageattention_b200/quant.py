@@ -68,19 +68,45 @@ def per_block_int8(q: torch.Tensor, k: torch.Tensor, km: Optional[torch.Tensor] 
     return q_int8, q_scale, k_int8, k_scale
 
 
+def quant_q_int8(q: torch.Tensor, qk_quant_gran: str = "per_thread", tensor_layout: str = "HND"):
+    """Q side of per_warp_int8 / per_thread_int8 (BLKQ=128, WARPQ=32): returns (q_int8, q_scale)."""
+    b, h_qo, qo_len, _ = _dims(q, tensor_layout)
+    lay = _layout(tensor_layout)
+    q_int8 = torch.empty(q.shape, dtype=torch.int8, device=q.device)
+    nblk = (qo_len + 127) // 128 * 4
+    if qk_quant_gran == "per_warp":
+        q_scale = torch.empty((b, h_qo, nblk), device=q.device, dtype=torch.float32)
+        ops.quant_per_block_int8(q, None, q_int8, q_scale, 32, lay, SAB_SEM_CUDA, False, 1.0)
+    else:
+        q_scale = torch.empty((b, h_qo, nblk * 8), device=q.device, dtype=torch.float32)
+        ops.quant_per_thread_int8(q, None, q_int8, q_scale, lay, False)
+    return q_int8, q_scale
+
+
+def quant_k_int8(k: torch.Tensor, km: Optional[torch.Tensor] = None, qk_quant_gran: str = "per_thread",
+                 tensor_layout: str = "HND"):
+    """K side of per_warp_int8 / per_thread_int8 (BLKK=64, WARPK=64) with the fused `k - km`: returns (k_int8, k_scale)."""
+    b, h_kv, kv_len, head_dim = _dims(k, tensor_layout)
+    lay = _layout(tensor_layout)
+    k_int8 = torch.empty(k.shape, dtype=torch.int8, device=k.device)
+    nblk = (kv_len + 63) // 64
+    mean = _squeeze_mean(km, b, h_kv, head_dim)
+    if qk_quant_gran == "per_warp":
+        k_scale = torch.empty((b, h_kv, nblk), device=k.device, dtype=torch.float32)
+        ops.quant_per_block_int8(k, mean, k_int8, k_scale, 64, lay, SAB_SEM_CUDA, False, 1.0)
+    else:
+        k_scale = torch.empty((b, h_kv, nblk * 4), device=k.device, dtype=torch.float32)
+        ops.quant_per_thread_int8(k, mean, k_int8, k_scale, lay, True)
+    return k_int8, k_scale
+
+
 def per_warp_int8(q: torch.Tensor, k: torch.Tensor, km: Optional[torch.Tensor] = None, BLKQ: int = 128,
                   WARPQ: int = 32, BLKK: int = 64, tensor_layout: str = "HND"):
     """sageattention/quant.py:105-180: q per WARPQ-row block, k per BLKK block with fused (k - km) in fp32;
     CUDA rounding semantics (cvt.rni, amax floored at 1e-7)."""
-    b, h_qo, qo_len, head_dim = _dims(q, tensor_layout)
-    _, h_kv, kv_len, _ = _dims(k, tensor_layout)
-    lay = _layout(tensor_layout)
-    q_int8 = torch.empty(q.shape, dtype=torch.int8, device=q.device)
-    k_int8 = torch.empty(k.shape, dtype=torch.int8, device=k.device)
-    q_scale = torch.empty((b, h_qo, ((qo_len + BLKQ - 1) // BLKQ) * (BLKQ // WARPQ)), device=q.device, dtype=torch.float32)
-    k_scale = torch.empty((b, h_kv, (kv_len + BLKK - 1) // BLKK), device=q.device, dtype=torch.float32)
-    ops.quant_per_block_int8(q, None, q_int8, q_scale, WARPQ, lay, SAB_SEM_CUDA, False, 1.0)
-    ops.quant_per_block_int8(k, _squeeze_mean(km, b, h_kv, head_dim), k_int8, k_scale, BLKK, lay, SAB_SEM_CUDA, False, 1.0)
+    assert BLKQ == 128 and WARPQ == 32 and BLKK == 64, "sm_100a kernel supports the reference defaults"
+    q_int8, q_scale = quant_q_int8(q, "per_warp", tensor_layout)
+    k_int8, k_scale = quant_k_int8(k, km, "per_warp", tensor_layout)
     return q_int8, q_scale, k_int8, k_scale
 
 
@@ -90,15 +116,8 @@ def per_thread_int8(q: torch.Tensor, k: torch.Tensor, km: Optional[torch.Tensor]
     """sageattention/triton/quant_per_thread.py:154-203 (8 q scales per 32-row block, 4 k scales per
     64-key block; `k - km` rounded to the input dtype first; scale = amax/127 + 1e-7)."""
     assert BLKQ == 128 and WARPQ == 32 and BLKK == 64 and WARPK == 64, "sm_100a kernel supports the reference defaults"
-    b, h_qo, qo_len, head_dim = _dims(q, tensor_layout)
-    _, h_kv, kv_len, _ = _dims(k, tensor_layout)
-    lay = _layout(tensor_layout)
-    q_int8 = torch.empty(q.shape, dtype=torch.int8, device=q.device)
-    k_int8 = torch.empty(k.shape, dtype=torch.int8, device=k.device)
-    q_scale = torch.empty((b, h_qo, (qo_len + BLKQ - 1) // BLKQ * (BLKQ // WARPQ) * 8), device=q.device, dtype=torch.float32)
-    k_scale = torch.empty((b, h_kv, (kv_len + BLKK - 1) // BLKK * (BLKK // WARPK) * 4), device=q.device, dtype=torch.float32)
-    ops.quant_per_thread_int8(q, None, q_int8, q_scale, lay, False)
-    ops.quant_per_thread_int8(k, _squeeze_mean(km, b, h_kv, head_dim), k_int8, k_scale, lay, True)
+    q_int8, q_scale = quant_q_int8(q, "per_thread", tensor_layout)
+    k_int8, k_scale = quant_k_int8(k, km, "per_thread", tensor_layout)
     return q_int8, q_scale, k_int8, k_scale
 
 

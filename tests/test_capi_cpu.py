@@ -71,3 +71,23 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("oracle/_ref", "").replace("the oracle", "").lower() or f == "build.py", f
+
+
+def test_extensions_beyond_the_reference_surface_are_exported_and_guarded():
+    """quantize_kv / sageattn_prequantized / sageattn_host: present, and never compute on CPU tensors."""
+    import torch
+    import sageattention_b200 as sab
+    for name in ("QuantizedKV", "quantize_kv", "sageattn_prequantized", "sageattn_host"):
+        assert hasattr(sab, name) and name in sab.__all__
+    k = torch.zeros(1, 2, 64, 64, dtype=torch.float16)
+    with pytest.raises(AssertionError):
+        sab.quantize_kv(k, k)                     # CPU tensors are not silently computed
+    with pytest.raises(ValueError):
+        sab.sageattn_host(k, k, k, tensor_layout="XYZ")
+    with pytest.raises(NotImplementedError):
+        sab.sageattn_host(k, k, k, return_lse=True)
+    with pytest.raises(AssertionError):
+        sab.sageattn_host(k.float(), k.float(), k.float())
+    from sageattention_b200.host import _chunks
+    assert _chunks(2, 8, 2, 4) == [(0, 0, 4), (0, 4, 8), (1, 0, 4), (1, 4, 8)]
+    assert _chunks(1, 6, 1, 4) == [(0, 0, 4), (0, 4, 6)]

@@ -394,6 +394,59 @@ def test_full_size_config3_varlen_gqa(env):
         assert (o[rows, h].float() - ex).abs().max().item() < 3e-2
 
 
+# ------------------------------------------------------------------------------------------- callers either side of the path (SURVEY §8 f)
+@pytest.mark.gpu
+def test_prequantized_kv_is_bit_identical_to_one_shot_call(env):
+    """quantize_kv once + sageattn_prequantized per call == sageattn_qk_int8_pv_fp8_cuda, bit for bit (same kernels)."""
+    sab, ops, O = env
+    cases = [dict(B=2, H=4, Hk=2, S=320, D=128, dt=torch.bfloat16, layout="HND", causal=False, gran="per_thread", acc="fp32+fp16"),
+             dict(B=1, H=4, Hk=4, S=257, D=64, dt=torch.float16, layout="NHD", causal=True, gran="per_warp", acc="fp32+fp32"),
+             dict(B=1, H=2, Hk=1, S=200, D=96, dt=torch.float16, layout="HND", causal=False, gran="per_thread", acc="fp32+fp16")]
+    for c in cases:
+        q, k, v = _mk(c["B"], c["H"], c["S"], c["D"], c["dt"], Hk=c["Hk"])
+        if c["layout"] == "NHD":
+            q, k, v = (t.transpose(1, 2).contiguous() for t in (q, k, v))
+        ref, ref_lse = sab.sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout=c["layout"], is_causal=c["causal"], qk_quant_gran=c["gran"],
+                                                        pv_accum_dtype=c["acc"], return_lse=True)
+        kv = sab.quantize_kv(k, v, tensor_layout=c["layout"], qk_quant_gran=c["gran"], pv_accum_dtype=c["acc"])
+        assert kv.kv_len == c["S"] and kv.nbytes() < (k.numel() + v.numel()) * k.element_size()
+        for _ in range(2):   # the cache is reusable
+            o, lse = sab.sageattn_prequantized(q, kv, is_causal=c["causal"], return_lse=True)
+            assert torch.equal(o, ref) and torch.equal(lse, ref_lse)
+        # a different query block against the same K/V (non-causal): equals the one-shot call on that block
+        if not c["causal"]:
+            q2 = torch.randn_like(q)[:, :, :130] if c["layout"] == "HND" else torch.randn_like(q)[:, :130]
+            q2 = q2.contiguous()
+            assert torch.equal(sab.sageattn_prequantized(q2, kv),
+                               sab.sageattn_qk_int8_pv_fp8_cuda(q2, k, v, tensor_layout=c["layout"], qk_quant_gran=c["gran"], pv_accum_dtype=c["acc"]))
+    with pytest.raises(AssertionError):
+        sab.sageattn_prequantized(q.to(torch.bfloat16), kv)
+
+
+@pytest.mark.gpu
+def test_host_pipeline_equals_device_call(env):
+    """sageattn_host (chunked H2D / compute / D2H pipeline over pinned host tensors) == sageattn on device copies."""
+    sab, ops, O = env
+    for (B, H, Hk, S, D, dt, layout, causal, hpc) in [(2, 8, 4, 384, 128, torch.bfloat16, "HND", False, 2),
+                                                      (2, 6, 6, 300, 64, torch.float16, "HND", True, 4),      # ragged last chunk
+                                                      (3, 4, 2, 256, 128, torch.float16, "NHD", False, None),
+                                                      (1, 4, 4, 200, 80, torch.bfloat16, "HND", False, 1)]:    # padded head dim
+        q, k, v = _mk(B, H, S, D, dt, Hk=Hk)
+        if layout == "NHD":
+            q, k, v = (t.transpose(1, 2).contiguous() for t in (q, k, v))
+        ref = sab.sageattn(q, k, v, tensor_layout=layout, is_causal=causal).cpu()
+        qh, kh, vh = (t.cpu().pin_memory() for t in (q, k, v))
+        out = sab.sageattn_host(qh, kh, vh, tensor_layout=layout, is_causal=causal, heads_per_chunk=hpc)
+        assert out.device.type == "cpu" and out.is_pinned() and torch.equal(out, ref)
+        # caller-provided (pageable) output, pageable inputs, sync=False + explicit stream sync
+        out2 = torch.empty_like(ref)
+        r = sab.sageattn_host(q.cpu(), k.cpu(), v.cpu(), out=out2, tensor_layout=layout, is_causal=causal, heads_per_chunk=hpc, sync=False)
+        torch.cuda.current_stream().synchronize()
+        assert r is out2 and torch.equal(out2, ref)
+    with pytest.raises(AssertionError):
+        sab.sageattn_host(q, k, v)   # device tensors belong to sageattn()
+
+
 # ------------------------------------------------------------------------------------------- sequence parallel (configs[4])
 def test_sequence_parallel_two_gpus(env):
     if torch.cuda.device_count() < 2:
