@@ -203,6 +203,24 @@ int sab_qk_int8_sv_f16_attn(const int8_t* q_int8, const int8_t* k_int8, const vo
                             const int32_t* cu_seqlens_k, const int32_t* cu_pad_v, const int32_t* cu_q_scale,
                             const int32_t* cu_k_scale, int max_seqlen_q, void* stream);
 
+/* Masked form of sab_qk_int8_sv_f16_attn: the `attn_mask` argument of sageattn_qk_int8_pv_fp16_triton
+ * (sageattention/core.py:160-331: bool or q.dtype, broadcast to [B,Hq,Sq,Skv], non-causal only) as consumed by
+ * sageattention/triton/attn_qk_int8_per_block.py:33-52:
+ *   SAB_MASK_BOOL : uint8 elements, 0 = masked out (the reference adds -1e6 and skips all-false blocks);
+ *   SAB_MASK_BIAS : additive bias in the output dtype (fp16 / bf16), added to S*scale in fp32 before the softmax.
+ * mask_stride_* are ELEMENT strides of the broadcast view (0 for broadcast dimensions).  Dense, non-causal, K scales
+ * per block / per warp; a row whose keys are all masked returns zeros (the reference: an unmasked softmax). */
+#define SAB_MASK_BOOL 1
+#define SAB_MASK_BIAS 2
+int sab_qk_int8_sv_f16_attn_masked(const int8_t* q_int8, const int8_t* k_int8, const void* v_f16t, void* out, float* lse,
+                                   const float* q_scale, const float* k_scale, int out_dtype, int B, int Hq, int Hkv,
+                                   int Sq, int Skv, int D, int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
+                                   int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_s, int64_t v_s_pad,
+                                   int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s, int q_gran, int k_gran,
+                                   float sm_scale, int fold_sm_scale, const void* attn_mask, int mask_kind,
+                                   int64_t mask_stride_b, int64_t mask_stride_h, int64_t mask_stride_m,
+                                   int64_t mask_stride_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -288,11 +288,13 @@ def attn_int8_fp8_cuda(q8, k8, v8, q_scale, k_scale, v_scale, *, qk_quant_gran="
 # attention: Triton fp16-PV path (per-block scales)
 # --------------------------------------------------------------------------------------------
 def attn_int8_fp16_triton(q8, k8, v, q_scale, k_scale, *, is_causal=False, out_dtype=torch.float16,
-                          BLOCK_M=128, BLOCK_N=64, return_lse=False):
+                          BLOCK_M=128, BLOCK_N=64, return_lse=False, attn_mask=None):
     """sageattention/triton/attn_qk_int8_per_block.py:22-128 and _causal.py:22-122.
     qk = dot(q,k).f32 * (q_scale*k_scale) [q already carries sm_scale*log2e]; OOB keys -1e6
     (non-causal, :53) / -inf (causal, :46); p = exp2(qk - m); l += sum(p) (fp32, l init 1.0 with
-    m init -inf -> alpha 0); acc = acc*alpha + dot(p.f16, v.f16, out_dtype=f16)."""
+    m init -inf -> alpha 0); acc = acc*alpha + dot(p.f16, v.f16, out_dtype=f16).
+    attn_mask (non-causal, :33-52): [B,Hq,Sq,Sk] bool -> qk += where(mask, 0, -1e6) and a 128 x 64 block with no True
+    element is skipped; otherwise an additive bias (promoted to fp32)."""
     B, Hq, Sq, D = q8.shape
     _, Hk, Sk, _ = k8.shape
     g = Hq // Hk
@@ -316,11 +318,21 @@ def attn_int8_fp16_triton(q8, k8, v, q_scale, k_scale, *, is_causal=False, out_d
             live = (qi[:, 0] >= s0)
         else:
             live = torch.ones(Sq, dtype=torch.bool)
+        lv = live[None, None, :]
+        if attn_mask is not None:
+            mb = attn_mask[:, :, :, s0:s1]
+            if attn_mask.dtype == torch.bool:
+                S = S + torch.where(mb, 0.0, -1.0e6)
+                # block skip (:35-36): per (b, h, 128-row block) when the whole block is False
+                nblk = (Sq + BLOCK_M - 1) // BLOCK_M
+                anyt = torch.stack([mb[:, :, i * BLOCK_M:(i + 1) * BLOCK_M].flatten(2).any(-1) for i in range(nblk)], dim=-1)
+                lv = anyt.repeat_interleave(BLOCK_M, dim=-1)[:, :, :Sq]
+            else:
+                S = S + mb.float()
         m_new = torch.maximum(m, S.amax(dim=-1))
         m_safe = torch.where(torch.isinf(m_new), torch.zeros_like(m_new), m_new)
         P = torch.exp2(S - m_safe[..., None])
         alpha = torch.where(torch.isinf(m_new), torch.ones_like(m), torch.exp2(m - m_safe))
-        lv = live[None, None, :]
         l = torch.where(lv, l * alpha + P.sum(-1), l)
         pv = (P.half().float() @ vf[:, :, s0:s1]).half().float()
         acc = torch.where(lv[..., None], acc * alpha[..., None] + pv, acc)
@@ -390,8 +402,8 @@ def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout="HND", is_causal=False,
 
 
 def sageattn_qk_int8_pv_fp16_triton(q, k, v, tensor_layout="HND", is_causal=False, sm_scale=None,
-                                    smooth_k=True, return_lse=False):
-    """sageattention/core.py:160-331 end to end (CPU; no attn_mask)."""
+                                    smooth_k=True, return_lse=False, attn_mask=None):
+    """sageattention/core.py:160-331 end to end (CPU); attn_mask: bool or q.dtype, broadcastable to [B,Hq,Sq,Sk]."""
     dtype = q.dtype
     q, k, v, hd_og = _pad_head_dim(q, k, v)
     seq_dim = 1 if tensor_layout == "NHD" else 2
@@ -406,7 +418,10 @@ def sageattn_qk_int8_pv_fp16_triton(q, k, v, tensor_layout="HND", is_causal=Fals
     q8, qs, k8, ks = per_block_int8_triton(q, k, km=km, sm_scale=sm_scale, tensor_layout=tensor_layout)
     o = attn_int8_fp16_triton(_to_hnd(q8, tensor_layout), _to_hnd(k8, tensor_layout),
                               _to_hnd(v, tensor_layout), qs, ks, is_causal=is_causal, out_dtype=dtype,
-                              return_lse=return_lse)
+                              return_lse=return_lse,
+                              attn_mask=None if attn_mask is None else attn_mask.expand(
+                                  _to_hnd(q, tensor_layout).shape[0], _to_hnd(q, tensor_layout).shape[1],
+                                  _to_hnd(q, tensor_layout).shape[2], _to_hnd(k, tensor_layout).shape[2]))
     lse = None
     if return_lse:
         o, lse = o

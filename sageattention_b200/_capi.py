@@ -10,6 +10,7 @@ _LIB_PATH = os.environ.get("SAB_LIB_PATH") or os.path.join(os.path.dirname(os.pa
 
 SAB_DTYPE_FP16, SAB_DTYPE_BF16 = 0, 1
 SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_WARP, SAB_GRAN_PER_THREAD = 1, 2, 3
+SAB_MASK_BOOL, SAB_MASK_BIAS = 1, 2
 SAB_SEM_CUDA, SAB_SEM_TRITON = 0, 1
 
 EXPORTS = {
@@ -33,6 +34,8 @@ EXPORTS = {
     "sab_v_transpose_f16": (c_int, [c_void_p, c_int, c_void_p] + [c_int] * 4 + [c_int64] * 4 + [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "sab_qk_int8_sv_f16_attn": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_int64] * 10 + [c_int, c_int, c_int, c_float, c_int] +
                                 [c_void_p] * 5 + [c_int, c_void_p]),
+    "sab_qk_int8_sv_f16_attn_masked": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_int64] * 10 + [c_int, c_int, c_float, c_int] +
+                                       [c_void_p, c_int] + [c_int64] * 4 + [c_void_p]),
     "sab_qk_int8_sv_f8_attn": (c_int, [c_void_p] * 9 + [c_int] * 7 + [c_int64] * 10 + [c_int, c_int, c_int, c_float, c_int] +
                                [c_void_p] * 5 + [c_int, c_int, c_int, c_void_p, c_void_p]),
 }

@@ -140,11 +140,15 @@ def sageattn_qk_int8_pv_fp16_triton(q, k, v, tensor_layout: str = "HND", quantiz
     """sageattention/core.py:160-331 on sm_100a: per-block INT8 quantisation with the Triton path's exact rounding
     (bit-exact q/k/scales), sm_scale*log2e folded into q, then the FP16-PV kernel variant (tcgen05 kind::f16, P and
     V in fp16, softmax without exponent offset — the Triton kernel's numerics, triton/attn_qk_int8_per_block.py).
-    attn_mask is not supported by the B200 kernel yet."""
-    if attn_mask is not None:
-        raise NotImplementedError("attn_mask is not supported by the sm_100a kernel yet")
+    attn_mask (bool, or the q dtype as an additive bias; broadcast to [B,Hq,Sq,Skv]; non-causal only) follows
+    core.py:248-250, 310-325 and attn_qk_int8_per_block.py:33-52 — including the reference's convention that a float
+    bias is added AFTER the logits were scaled by sm_scale*log2(e), i.e. it acts as bias*ln(2) in natural-log units."""
     dtype = q.dtype
     _check_inputs(q, k, v)
+    if attn_mask is not None:
+        assert attn_mask.dtype == torch.bool or attn_mask.dtype == q.dtype, "attn_mask must be of dtype bool or the same dtype as q."
+        assert attn_mask.device == q.device, "All tensors must be on the same device."
+        assert not is_causal, "Mask should be None for causal attention."
     _tensor_layout = 0 if tensor_layout == "NHD" else 1
     q, k, v, head_dim_og = _pad_head_dim(q, k, v)
     assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of qkv must be contiguous."
@@ -163,8 +167,20 @@ def sageattn_qk_int8_pv_fp16_triton(q, k, v, tensor_layout: str = "HND", quantiz
                                                       semantics=quantization_backend)
     v_t = transpose_v_f16(v, tensor_layout=tensor_layout)       # `v.to(torch.float16)`, core.py:297-298
     o = torch.empty(q.size(), dtype=dtype, device=q.device)
-    lse = ops.qk_int8_sv_f16_attn(q_int8, k_int8, v_t, o, q_scale, k_scale, _tensor_layout, 1 if is_causal else 0,
-                                  SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_BLOCK, sm_scale, 1, 1 if return_lse else 0)
+    if attn_mask is not None:
+        if tensor_layout == "HND":
+            target_shape = (q.shape[0], q.shape[1], q.shape[2], k.shape[2])
+        else:
+            target_shape = (q.shape[0], q.shape[2], q.shape[1], k.shape[1])
+        try:
+            attn_mask = attn_mask.expand(target_shape)     # core.py:314-323; a view: broadcast dims get stride 0
+        except Exception:
+            raise AssertionError(f"attn_mask shape {attn_mask.shape} cannot be broadcast to {target_shape}")
+        lse = ops.qk_int8_sv_f16_attn_masked(q_int8, k_int8, v_t, o, q_scale, k_scale, attn_mask, _tensor_layout,
+                                             SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_BLOCK, sm_scale, 1, 1 if return_lse else 0)
+    else:
+        lse = ops.qk_int8_sv_f16_attn(q_int8, k_int8, v_t, o, q_scale, k_scale, _tensor_layout, 1 if is_causal else 0,
+                                      SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_BLOCK, sm_scale, 1, 1 if return_lse else 0)
     o = o[..., :head_dim_og]
     if return_lse:
         return o, lse / _LOG2E + lse_correction * sm_scale if smooth_k else lse / _LOG2E

@@ -26,7 +26,9 @@ constexpr int kNumThreads = 384;  // warpgroups: 0-3 softmax, 4-7 correction, 8 
 // D: head dim (64 / 128).  kKT: per-thread K scales (4 per 64-key block) instead of 1.  OutT: __half / bf16.
 // kPV16: P and V in fp16 (tcgen05 kind::f16) with the Triton path's softmax (no exponent offset) — the numerics of the
 // reference's sageattn_qk_int8_pv_fp16_triton / sageattn_varlen kernels (triton/attn_qk_int8_per_block.py:22-128).
-template <int D, bool kKT, typename OutT, bool kPV16>
+// kMask (kPV16 only): attn_mask of sageattn_qk_int8_pv_fp16_triton — a bool mask marks elements like the out-of-range
+// keys (integer sentinel), an additive bias takes the float path `tile_bias` below.
+template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false>
 __global__ void __launch_bounds__(kNumThreads, 2)
 sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -273,6 +275,19 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int i = 0; i < BN; ++i) p.dbg[row * BN + i] = int(s[i]);
       }
 
+      [[maybe_unused]] const char* mrow = nullptr;   // this row's 64 mask elements of tile j
+      if constexpr (kMask) {
+        const int64_t off = int64_t(b) * p.mask_sb + int64_t(h) * p.mask_sh + int64_t(q_row) * p.mask_sm + int64_t(j) * BN * p.mask_sn;
+        mrow = reinterpret_cast<const char*>(p.mask) + off * (p.mask_kind == 1 ? 1 : 2);
+        if (q_row >= q_len) limit = 0;   // rows past the end: nothing visible, no mask bytes read
+        if (p.mask_kind == 1) {
+#pragma unroll
+          for (int i = 0; i < BN; ++i) {
+            if (i < limit && __ldg(reinterpret_cast<const uint8_t*>(mrow) + int64_t(i) * p.mask_sn) == 0) s[i] = uint32_t(kIntSentinel);
+          }
+        }
+      }
+
       auto tile = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
         // ---- row max.  Scales are positive, so max_c(S_c*coef_g(c)) = max_g(coef_g * max_{c in g} S_c): integer
@@ -342,7 +357,10 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             e[u] = ex2_approx(y0);
             e[u + 1] = ex2_approx(y1);
 #endif
-            if constexpr (MASKED) {
+            if constexpr (MASKED && kMask) {   // masked-out elements are not a prefix of the tile
+              e[u] = (int(s[i]) != kIntSentinel) ? e[u] : 0.f;
+              e[u + 1] = (int(s[i + 1]) != kIntSentinel) ? e[u + 1] : 0.f;
+            } else if constexpr (MASKED) {
               e[u] = (i < limit) ? e[u] : 0.f;
               e[u + 1] = (i + 1 < limit) ? e[u + 1] : 0.f;
             }
@@ -369,7 +387,41 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int w = 0; w < BN / 4; ++w) p.dbg[128 * BN + row * 16 + w] = int(pk[w]);
         }
       };
-      if (masked_tile) tile(std::true_type{});
+      // additive bias (attn_qk_int8_per_block.py:41,50-51): qk = S*scale + bias in fp32, then the plain online softmax
+      auto tile_bias = [&]() {
+        if constexpr (kMask && kPV16) {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < BN; ++i) {
+            float y = -INFINITY;
+            if (i < limit) {
+              const float bias = float(__ldg(reinterpret_cast<const OutT*>(mrow) + int64_t(i) * p.mask_sn));
+              y = fmaf(__int2float_rn(int(s[i])), coef[kKT ? ((i & 7) >> 1) : 0], bias);
+            }
+            s[i] = __float_as_uint(y);
+            mx = fmaxf(mx, y);
+          }
+          const float m_new = fmaxf(m, mx);     // m starts at the finite mask value: never -inf
+          const float alpha = ex2_approx(m - m_new);
+          d *= alpha;
+          m = m_new;
+          s_alpha[(j & 1) * BM + row] = alpha;
+          mbar_arrive(a_full + (j & 1));
+          uint32_t pk[PCOLS];
+          float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < BN; i += 2) {
+            const float e0 = ex2_approx(__uint_as_float(s[i]) - m_new), e1 = ex2_approx(__uint_as_float(s[i + 1]) - m_new);
+            sum0 += e0;
+            sum1 += e1;
+            pk[i / 2] = pack_f16x2(e0, e1);
+          }
+          d += sum0 + sum1;
+          tmem_st32(tS, pk);
+        }
+      };
+      if (kMask && p.mask_kind == 2) tile_bias();
+      else if (kMask || masked_tile) tile(std::true_type{});
       else tile(std::false_type{});
 
       SAB_TL(5);
@@ -389,7 +441,7 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (n_kv > 0) {
       mbar_wait_wd(s_full + ((n_kv + 1) & 1), s_parity(n_kv + 1));   // step(n_kv-1) retired: O is final
       tc_fence_after();
-      const float inv = rcp_approx(d);
+      const float inv = (kMask && !(d > 0.f)) ? 0.f : rcp_approx(d);   // a fully masked row yields zeros, not NaN
 #pragma unroll
       for (int ch = 0; ch < D / 32; ++ch) {
         uint32_t r[32];
@@ -515,7 +567,7 @@ template <int D, bool kKT, typename OutT>
 int launch_attn_split(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                       cudaStream_t stream);
 
-template <int D, bool kKT, typename OutT, bool kPV16>
+template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
   if (!kPV16 && use_pair_kernel()) {
@@ -532,7 +584,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   // Q tile + NS x (K + V^T 64-key tile) + alpha hand-off + barriers (97.5 KB at hd128): two CTAs per SM (TMEM: 2 x 256 columns)
   size_t smem = size_t(BM) * D + size_t(NS) * (BN * D + BN * D * (kPV16 ? 2 : 1)) + 2 * BM * sizeof(float) + 512;
   if (smem < 80 * 1024) smem = 80 * 1024;
-  auto kern = sage_attn_fwd_kernel<D, kKT, OutT, kPV16>;
+  auto kern = sage_attn_fwd_kernel<D, kKT, OutT, kPV16, kMask>;
   static bool configured = false;
   if (!configured) {
     SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -544,6 +596,12 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 }
 
 }  // namespace sab
+
+// attention mask of the masked entry point, handed to attn_entry by sab_qk_int8_sv_f16_attn_masked (same thread)
+struct MaskArgs {
+  const void* ptr; int kind; int64_t sb, sh, sm, sn;
+};
+static thread_local const MaskArgs* tl_mask = nullptr;
 
 static int attn_entry(int pv16, const int8_t* q_int8, const int8_t* k_int8, const uint8_t* v_fp8, void* out,
                                       float* lse, const float* q_scale, const float* k_scale, const float* v_scale,
@@ -623,6 +681,21 @@ static int attn_entry(int pv16, const int8_t* q_int8, const int8_t* k_int8, cons
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool kt = k_gran == SAB_GRAN_PER_THREAD;
   const bool bf = out_dtype == SAB_DTYPE_BF16;
+  if (tl_mask != nullptr) {
+    // attn_qk_int8_per_block.py:33-52 (non-causal kernel only; sageattention/core.py:310-325 asserts mask is None when causal)
+    SAB_REQUIRE(pv16 && !kt && !varlen && !is_causal, SAB_ERR_UNSUPPORTED,
+                "attn_mask is supported by the dense non-causal fp16-PV path with per-block / per-warp K scales only");
+    SAB_REQUIRE(tl_mask->ptr != nullptr && (tl_mask->kind == SAB_MASK_BOOL || tl_mask->kind == SAB_MASK_BIAS), SAB_ERR_INVALID,
+                "attn_mask: null pointer or unknown kind %d", tl_mask->kind);
+    p.mask = tl_mask->ptr; p.mask_kind = tl_mask->kind;
+    p.mask_sb = tl_mask->sb; p.mask_sh = tl_mask->sh; p.mask_sm = tl_mask->sm; p.mask_sn = tl_mask->sn;
+    if (D == 128) {
+      if (bf) return launch_attn<128, false, __nv_bfloat16, true, true>(tq, tk, tv, p, grid, s);
+      return launch_attn<128, false, __half, true, true>(tq, tk, tv, p, grid, s);
+    }
+    if (bf) return launch_attn<64, false, __nv_bfloat16, true, true>(tq, tk, tv, p, grid, s);
+    return launch_attn<64, false, __half, true, true>(tq, tk, tv, p, grid, s);
+  }
 #define SAB_LAUNCH(DD, KT, T)                                                      \
   do {                                                                             \
     if (pv16) return launch_attn<DD, KT, T, true>(tq, tk, tv, p, grid, s);         \
@@ -667,4 +740,22 @@ extern "C" int sab_qk_int8_sv_f16_attn(const int8_t* q_int8, const int8_t* k_int
                     out_dtype, B, Hq, Hkv, Sq, Skv, D, q_stride_b, q_stride_h, q_stride_s, k_stride_b, k_stride_h, k_stride_s,
                     v_s_pad, o_stride_b, o_stride_h, o_stride_s, is_causal, q_gran, k_gran, sm_scale, fold_sm_scale,
                     cu_seqlens_q, cu_seqlens_k, cu_pad_v, cu_q_scale, cu_k_scale, max_seqlen_q, 0, 0, nullptr, stream);
+}
+
+extern "C" int sab_qk_int8_sv_f16_attn_masked(const int8_t* q_int8, const int8_t* k_int8, const void* v_f16t, void* out, float* lse,
+                                              const float* q_scale, const float* k_scale, int out_dtype, int B, int Hq, int Hkv,
+                                              int Sq, int Skv, int D, int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
+                                              int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_s, int64_t v_s_pad,
+                                              int64_t o_stride_b, int64_t o_stride_h, int64_t o_stride_s, int q_gran, int k_gran,
+                                              float sm_scale, int fold_sm_scale, const void* attn_mask, int mask_kind,
+                                              int64_t mask_stride_b, int64_t mask_stride_h, int64_t mask_stride_m,
+                                              int64_t mask_stride_n, void* stream) {
+  const MaskArgs m{attn_mask, mask_kind, mask_stride_b, mask_stride_h, mask_stride_m, mask_stride_n};
+  tl_mask = &m;
+  const int st = attn_entry(1, q_int8, k_int8, reinterpret_cast<const uint8_t*>(v_f16t), out, lse, q_scale, k_scale, nullptr,
+                            nullptr, out_dtype, B, Hq, Hkv, Sq, Skv, D, q_stride_b, q_stride_h, q_stride_s, k_stride_b,
+                            k_stride_h, k_stride_s, v_s_pad, o_stride_b, o_stride_h, o_stride_s, 0, q_gran, k_gran, sm_scale,
+                            fold_sm_scale, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, nullptr, stream);
+  tl_mask = nullptr;
+  return st;
 }

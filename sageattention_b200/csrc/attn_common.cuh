@@ -51,6 +51,10 @@ struct AttnParams {
   int causal_q_offset;   // global index of query row 0 (sequence-parallel causal)
   int kv_seg_len;        // > 0: K/V are rank-major all-gathered segments of this many keys
   int32_t* dbg;          // nullable debug dump (CTA 0 only)
+  // attention mask of the Triton-path shell (attn_qk_int8_per_block.py:33-52): [B,Hq,Sq,Skv] with arbitrary (also 0) strides
+  const void* mask;      // nullable
+  int mask_kind;         // 1: bool (uint8, false = masked out), 2: additive bias in the output dtype (fp16 / bf16)
+  int64_t mask_sb, mask_sh, mask_sm, mask_sn;   // element strides
 };
 
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {

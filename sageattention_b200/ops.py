@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 
 from . import _capi
-from ._capi import check, lib
+from ._capi import check, lib, SAB_MASK_BOOL, SAB_MASK_BIAS
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -285,6 +285,40 @@ def qk_int8_sv_f16_attn(query: torch.Tensor, key: torch.Tensor, value: torch.Ten
 
 @qk_int8_sv_f16_attn.register_fake
 def _(query, key, value, output, query_scale, key_scale, tensor_layout, is_causal, q_quant_gran, k_quant_gran, sm_scale,
+      fold_sm_scale, return_lse):
+    B, Hq, Sq, D = _bhsd(query, tensor_layout)
+    if return_lse:
+        return torch.empty((B, Hq, Sq), dtype=torch.float32, device=query.device)
+    return torch.empty((0,), dtype=torch.float32, device=query.device)
+
+
+@torch.library.custom_op("sageattention_b200::qk_int8_sv_f16_attn_masked", mutates_args=("output",), device_types="cuda")
+def qk_int8_sv_f16_attn_masked(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, output: torch.Tensor,
+                               query_scale: torch.Tensor, key_scale: torch.Tensor, attn_mask: torch.Tensor, tensor_layout: int,
+                               q_quant_gran: int, k_quant_gran: int, sm_scale: float, fold_sm_scale: int,
+                               return_lse: int) -> torch.Tensor:
+    """qk_int8_sv_f16_attn with the Triton path's attn_mask: a 4-D view broadcast to [B,Hq,Sq,Skv] (strides may be 0),
+    dtype bool (False = masked out) or the q dtype (additive bias).  Non-causal (sageattention/core.py:310)."""
+    B, Hq, Sq, D = _bhsd(query, tensor_layout)
+    _, Hkv, Skv, _ = _bhsd(key, tensor_layout)
+    assert attn_mask.dim() == 4 and tuple(attn_mask.shape) == (B, Hq, Sq, Skv), "attn_mask must be expanded to [B,Hq,Sq,Skv]"
+    kind = SAB_MASK_BOOL if attn_mask.dtype == torch.bool else SAB_MASK_BIAS
+    assert kind == SAB_MASK_BOOL or attn_mask.dtype == output.dtype, "attn_mask must be bool or the q / output dtype"
+    qs, ks, os_ = _bhs_strides(query, tensor_layout), _bhs_strides(key, tensor_layout), _bhs_strides(output, tensor_layout)
+    lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=query.device) if return_lse else \
+        torch.empty((0,), dtype=torch.float32, device=query.device)
+    with torch.cuda.device(query.device):
+        check(lib().sab_qk_int8_sv_f16_attn_masked(query.data_ptr(), key.data_ptr(), value.data_ptr(), output.data_ptr(),
+                                                   lse.data_ptr() if return_lse else None, query_scale.data_ptr(),
+                                                   key_scale.data_ptr(), _dt(output), B, Hq, Hkv, Sq, Skv, D, *qs, *ks,
+                                                   value.size(-1), *os_, q_quant_gran, k_quant_gran, float(sm_scale),
+                                                   fold_sm_scale, attn_mask.data_ptr(), kind, *attn_mask.stride(),
+                                                   _stream(query)))
+    return lse
+
+
+@qk_int8_sv_f16_attn_masked.register_fake
+def _(query, key, value, output, query_scale, key_scale, attn_mask, tensor_layout, q_quant_gran, k_quant_gran, sm_scale,
       fold_sm_scale, return_lse):
     B, Hq, Sq, D = _bhsd(query, tensor_layout)
     if return_lse:

@@ -43,8 +43,10 @@ def main():
     att, attc = load("attn_qk_int8_per_block"), load("attn_qk_int8_per_block_causal")
     attv, attvc = load("attn_qk_int8_block_varlen"), load("attn_qk_int8_per_block_causal_varlen")
 
+    only_mask = "--only-mask" in sys.argv      # regenerate just the attn_mask fixtures (section 2b)
+
     # ---- 1. quantisation fixtures (bit-exact targets) ----------------------------------------
-    for name, shape, dtype, outlier in [
+    for name, shape, dtype, outlier in [] if only_mask else [
         ("quant_d64_fp16", (1, 2, 200, 64), torch.float16, True),
         ("quant_d128_bf16", (2, 2, 333, 128), torch.bfloat16, False),
     ]:
@@ -64,7 +66,7 @@ def main():
         print("wrote", name)
 
     # ---- 2. Triton attention path (sageattn_qk_int8_pv_fp16_triton internals, core.py:260-331) ----
-    for name, shape, dtype, causal in [
+    for name, shape, dtype, causal in [] if only_mask else [
         ("attn_d64_fp16_nc", (1, 2, 320, 64), torch.float16, False),
         ("attn_d64_fp16_c", (1, 2, 320, 64), torch.float16, True),
         ("attn_d128_fp16_nc_ragged", (1, 2, 200, 128), torch.float16, False),
@@ -81,6 +83,34 @@ def main():
         np.savez_compressed(f"{HERE}/{name}.npz", q=bits(q), k=bits(k), v=bits(v), o=bits(o),
                             lse=lse.numpy(), causal=causal, dtype=str(dtype))
         print("wrote", name)
+
+    # ---- 2b. attn_mask of the Triton path (core.py:248-250, 310-325; attn_qk_int8_per_block.py:33-52) ----
+    for name, shape, kind in [("attn_mask_bool_d64", (1, 2, 256, 64), "bool"), ("attn_mask_bias_d128", (1, 2, 200, 128), "bias")]:
+        dtype = torch.float16
+        q, k, v = mk(shape, dtype, 4242, True)
+        B, H, S, D = shape
+        g = torch.Generator().manual_seed(17)
+        if kind == "bool":
+            mask = torch.rand((1, 1, S, S), generator=g) < 0.6           # broadcast over heads (stride 0 after expand)
+            mask[:, :, :128, 64:128] = False                             # one all-false 128 x 64 block: the reference skips it
+            mask[:, :, :, 0] = True                                      # every row keeps at least one key
+        else:
+            mask = torch.randn((1, H, S, S), generator=g)
+            mask[torch.rand((1, H, S, S), generator=g) < 0.3] = -30000.0  # "minus infinity" of fp16 pipelines
+            mask[:, :, :, 0] = 0.0
+            mask = mask.to(dtype)
+        km = k.mean(dim=2, keepdim=True)
+        lse_corr = torch.matmul(q, km.transpose(2, 3)).squeeze(-1).to(torch.float32)
+        sm_scale = 1.0 / (D ** 0.5)
+        q8, qs, k8, ks = qpb.per_block_int8(q, k, km=km, sm_scale=sm_scale)
+        o, lse = att.forward(q8, k8, v, qs, ks, tensor_layout="HND", output_dtype=dtype, attn_mask=mask.expand(B, H, S, S), return_lse=True)
+        lse = lse / 1.44269504 + lse_corr * sm_scale
+        mk_arr = mask.numpy() if kind == "bool" else bits(mask)
+        np.savez_compressed(f"{HERE}/{name}.npz", q=bits(q), k=bits(k), v=bits(v), o=bits(o), lse=lse.numpy(), mask=mk_arr,
+                            mask_shape=np.array(mask.shape), kind=kind, dtype=str(dtype))
+        print("wrote", name)
+    if only_mask:
+        return
 
     # ---- 3. varlen (core.py:399-448) ---------------------------------------------------------
     for name, causal in [("varlen_gqa_d128_nc", False), ("varlen_gqa_d128_c", True)]:

@@ -50,6 +50,29 @@ def test_triton_attention_path(name):
     assert (o.float() - exact).abs().max().item() < 5e-2
 
 
+def _load_mask(z, dt):
+    shape = tuple(int(x) for x in z["mask_shape"])
+    if str(z["kind"]) == "bool":
+        return torch.from_numpy(z["mask"].copy()).view(shape)
+    return _t(z["mask"], dt).view(shape)
+
+
+@pytest.mark.parametrize("name", ["attn_mask_bool_d64", "attn_mask_bias_d128"])
+def test_triton_attention_path_with_attn_mask(name):
+    """attn_mask of sageattn_qk_int8_pv_fp16_triton: bool (with one all-false block the reference skips, broadcast over
+    heads) and additive fp16 bias, against the reference Triton kernel's output."""
+    z = np.load(f"{G}/{name}.npz")
+    dt = _dtype(z["dtype"])
+    q, k, v, o_ref = (_t(z[n], dt) for n in ("q", "k", "v", "o"))
+    mask = _load_mask(z, dt)
+    o, lse = O.sageattn_qk_int8_pv_fp16_triton(q, k, v, return_lse=True, attn_mask=mask)
+    assert (o.float() - o_ref.float()).abs().max().item() < 2e-3
+    assert np.allclose(lse.numpy(), z["lse"], atol=2e-4, rtol=1e-5)
+    # the mask matters: the unmasked result is far away
+    o_nomask = O.sageattn_qk_int8_pv_fp16_triton(q, k, v)
+    assert (o_nomask.float() - o_ref.float()).abs().max().item() > 5e-2
+
+
 @pytest.mark.parametrize("name", ["varlen_gqa_d128_nc", "varlen_gqa_d128_c"])
 def test_varlen_path(name):
     z = np.load(f"{G}/{name}.npz")
