@@ -161,3 +161,53 @@ def sageattn_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout
                                sm_scale, 0, 0, rank * Sl, Sl)
     o = o[..., :head_dim_og]
     return o if lay == 1 else o.transpose(1, 2)
+
+
+# ------------------------------------------------------------------ Ulysses (head-parallel) variant, SURVEY §8e / f-3
+def _seq_to_head_shard(x: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """[B,H,S/P,D] on every rank (sequence-sharded) -> [B,H/P,S,D] (head-sharded): one all_to_all."""
+    B, H, Sl, D = x.shape
+    send = x.reshape(B, world, H // world, Sl, D).permute(1, 0, 2, 3, 4).contiguous()     # [P(dst rank = head group),B,H/P,Sl,D]
+    recv = torch.empty_like(send)                                                        # [P(src rank = sequence slice),...]
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.permute(1, 2, 0, 3, 4).reshape(B, H // world, world * Sl, D)
+
+
+def _head_to_seq_shard(x: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """inverse of _seq_to_head_shard: [B,H/P,S,D] -> [B,H,S/P,D]."""
+    B, Hl, S, D = x.shape
+    Sl = S // world
+    send = x.reshape(B, Hl, world, Sl, D).permute(2, 0, 1, 3, 4).contiguous()             # [P(dst rank = sequence slice),B,H/P,Sl,D]
+    recv = torch.empty_like(send)                                                        # [P(src rank = head group),...]
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.permute(1, 0, 2, 3, 4).reshape(B, world * Hl, Sl, D)
+
+
+def sageattn_ulysses(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout: str = "HND", is_causal: bool = False,
+                     sm_scale: Optional[float] = None, group=None, attn_fn=None, **kwargs: Any) -> torch.Tensor:
+    """Ulysses sequence parallelism around `sageattn` (what the reference's example delegates to xfuser,
+    example/parallel_sageattn_cogvideo.py:32-51): every rank holds a sequence slice of ALL heads; an all_to_all turns that
+    into the FULL sequence of H/P heads, the unmodified single-GPU `sageattn` runs on those heads, a second all_to_all
+    restores the sequence sharding of the output.  No numerics change at all (K mean, V scales and block scales are per
+    head), so each head's result is bit-identical to the single-GPU call.  Needs Hq % P == 0 and Hkv % P == 0; use
+    `sageattn_sp` (KV all-gather of 8-bit tensors) otherwise — it also moves half the bytes.
+    attn_fn: the local attention callable (default: sageattn_qk_int8_pv_fp8_cuda, the operator behind sageattn); tests
+    inject the CPU oracle under gloo."""
+    if not dist.is_initialized():
+        raise RuntimeError("sageattn_ulysses needs an initialised torch.distributed process group")
+    world = dist.get_world_size(group)
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    if attn_fn is None:
+        from .core import sageattn_qk_int8_pv_fp8_cuda as attn_fn     # what sageattn dispatches to; honours qk_quant_gran etc.
+    hnd = tensor_layout == "HND"
+    qh, kh, vh = (t if hnd else t.transpose(1, 2) for t in (q, k, v))
+    Hq, Hk = qh.size(1), kh.size(1)
+    assert Hq % world == 0 and Hk % world == 0, f"Ulysses needs num heads ({Hq}, {Hk}) divisible by the group size {world}"
+    assert qh.size(2) == kh.size(2) or not is_causal, "qo_len and kv_len must be equal for causal attention."
+    if world == 1:
+        return attn_fn(q, k, v, tensor_layout=tensor_layout, is_causal=is_causal, sm_scale=sm_scale, **kwargs)
+    qf, kf, vf = (_seq_to_head_shard(t, world, group) for t in (qh, kh, vh))
+    of = attn_fn(qf, kf, vf, tensor_layout="HND", is_causal=is_causal, sm_scale=sm_scale, **kwargs)
+    o = _head_to_seq_shard(of.contiguous(), world, group)
+    return o if hnd else o.transpose(1, 2)

@@ -30,6 +30,13 @@ for (B, H, Hk, S, D, causal, gran) in [(1, 4, 4, 1024 * world, 128, False, "per_
     err_n = (o_sp_n.transpose(1, 2).float() - o_sp.float()).abs().max().item()
     print(f"rank {rank} cfg {(B, H, Hk, S, D, causal, gran)} max-abs SP vs single {err:.3e}  NHD vs HND {err_n:.3e}", flush=True)
     ok = ok and err <= 4e-3 and err_n == 0.0     # K mean summation order may differ in the last fp32 bit -> rare 1-ulp km differences
+    # Ulysses (head-parallel, two all_to_all): per-head statistics only -> bit-identical to the single-GPU call
+    if H % world == 0 and Hk % world == 0:
+        o_u = parallel.sageattn_ulysses(q[:, :, sl].contiguous(), k[:, :, sl].contiguous(), v[:, :, sl].contiguous(), is_causal=causal,
+                                        qk_quant_gran=gran)
+        same = torch.equal(o_u, o_1)
+        print(f"rank {rank} ulysses == single-GPU: {same}", flush=True)
+        ok = ok and same
 t = torch.tensor([1.0 if ok else 0.0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0 and t.item() == 1.0:

@@ -47,3 +47,46 @@ def test_sp_host_logic_gloo_world2():
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     for r in range(world):
         assert all(ret[r]), f"rank {r}: {ret[r]}"
+
+
+def _ulysses_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sageattention_b200 import parallel
+    from oracle import sage_oracle as O
+    torch.manual_seed(0)
+    B, H, Hk, S, D = 1, 4, 2, 256, 64
+    q = torch.randn(B, H, S, D).half()
+    k = (torch.randn(B, Hk, S, D) + 2.0 * torch.randn(B, Hk, 1, D)).half()
+    v = torch.randn(B, Hk, S, D).half()
+    Sl = S // world
+    sl = slice(rank * Sl, (rank + 1) * Sl)
+    oks = []
+    for layout, causal in (("HND", False), ("NHD", True)):
+        full = O.sageattn_qk_int8_pv_fp8_cuda(q, k, v, is_causal=causal)                      # single-process result, HND
+        ql, kl, vl = q[:, :, sl], k[:, :, sl], v[:, :, sl]
+        if layout == "NHD":
+            ql, kl, vl = (t.transpose(1, 2).contiguous() for t in (ql, kl, vl))
+        o = parallel.sageattn_ulysses(ql, kl, vl, tensor_layout=layout, is_causal=causal, attn_fn=O.sageattn_qk_int8_pv_fp8_cuda)
+        if layout == "NHD":
+            o = o.transpose(1, 2)
+        oks.append(torch.equal(o, full[:, :, sl]))     # per-head statistics only: bit-identical to the unsharded call
+    # the two all_to_all re-layouts are inverses and put sequence slices in rank order
+    x = torch.rand(B, H, Sl, D).floor() + float(rank)             # every element == the owning rank
+    y = parallel._seq_to_head_shard(x, world)
+    oks.append(y.shape == (B, H // world, S, D) and bool((y[:, :, :Sl] == 0.0).all()) and bool((y[:, :, Sl:] == 1.0).all()))
+    x2 = torch.randn(B, H, Sl, D)
+    oks.append(torch.equal(parallel._head_to_seq_shard(parallel._seq_to_head_shard(x2, world), world), x2))
+    ret[rank] = tuple(oks)
+    dist.destroy_process_group()
+
+
+def test_ulysses_head_parallel_gloo_world2():
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ulysses_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert all(ret[r]), f"rank {r}: {ret[r]}"
