@@ -191,8 +191,8 @@ def sageattn_ulysses(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_l
     restores the sequence sharding of the output.  No numerics change at all (K mean, V scales and block scales are per
     head), so each head's result is bit-identical to the single-GPU call.  Needs Hq % P == 0 and Hkv % P == 0; use
     `sageattn_sp` (KV all-gather of 8-bit tensors) otherwise — it also moves half the bytes.
-    attn_fn: the local attention callable (default: sageattn_qk_int8_pv_fp8_cuda, the operator behind sageattn); tests
-    inject the CPU oracle under gloo."""
+    attn_fn: the local attention callable (default: sageattn_qk_int8_pv_fp8_cuda, the operator behind sageattn); the gloo tests
+    inject a CPU stand-in."""
     if not dist.is_initialized():
         raise RuntimeError("sageattn_ulysses needs an initialised torch.distributed process group")
     world = dist.get_world_size(group)
