@@ -211,3 +211,57 @@ def sageattn_ulysses(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_l
     of = attn_fn(qf, kf, vf, tensor_layout="HND", is_causal=is_causal, sm_scale=sm_scale, **kwargs)
     o = _head_to_seq_shard(of.contiguous(), world, group)
     return o if hnd else o.transpose(1, 2)
+
+
+# ------------------------------------------------------------------ ring attention over return_lse, SURVEY §8 f-3
+def merge_attention_states(o_a: torch.Tensor, lse_a: torch.Tensor, o_b: torch.Tensor, lse_b: torch.Tensor, hnd: bool = True):
+    """Combine two partial attention results over disjoint key sets from their natural-log LSEs (the use the reference
+    gives `return_lse`, sageattention/core.py:289-293, 329): softmax weights of the union = exp(lse_x - logaddexp)."""
+    lse = torch.logaddexp(lse_a, lse_b)
+    wa, wb = torch.exp(lse_a - lse), torch.exp(lse_b - lse)                 # [B,H,S]
+    if not hnd:
+        wa, wb = wa.transpose(1, 2), wb.transpose(1, 2)
+    o = o_a.float() * wa.unsqueeze(-1) + o_b.float() * wb.unsqueeze(-1)
+    return o, lse
+
+
+def sageattn_ring(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout: str = "HND", is_causal: bool = False,
+                  sm_scale: Optional[float] = None, group=None, attn_fn=None, **kwargs: Any) -> torch.Tensor:
+    """Ring attention: Q stays put, the K/V slices travel round the ring (P-1 send/recv steps, bf16/fp16 payload), each
+    step is one `sageattn(..., return_lse=True)` on the local Q slice against the visiting K/V slice and the partial
+    results are merged through their LSEs.  For sequences whose gathered K/V do not fit one GPU; otherwise prefer
+    `sageattn_sp` (one 8-bit gather, one kernel) — this form quantises every visiting slice again and smooths K per
+    slice (the LSE returned by the operator is already corrected to the unsmoothed keys, core.py:329), so its result
+    agrees with the single-GPU call to quantisation accuracy, not bit for bit.
+    Causal: slices from later ranks are skipped, the diagonal slice runs causal, earlier slices run unmasked."""
+    if not dist.is_initialized():
+        raise RuntimeError("sageattn_ring needs an initialised torch.distributed process group")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if tensor_layout not in ("HND", "NHD"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    if attn_fn is None:
+        from .core import sageattn_qk_int8_pv_fp8_cuda as attn_fn
+    hnd = tensor_layout == "HND"
+    k_cur, v_cur = k.contiguous(), v.contiguous()
+    o_acc, lse_acc = None, None
+    for step in range(world):
+        src = (rank - step) % world                       # owner of the K/V slice held in this step
+        reqs = []
+        if step + 1 < world:                              # pass the slice on while computing with it
+            k_nxt, v_nxt = torch.empty_like(k_cur), torch.empty_like(v_cur)
+            nxt, prv = (rank + 1) % world, (rank - 1) % world
+            ops_ = [dist.P2POp(dist.isend, k_cur, nxt, group), dist.P2POp(dist.isend, v_cur, nxt, group),
+                    dist.P2POp(dist.irecv, k_nxt, prv, group), dist.P2POp(dist.irecv, v_nxt, prv, group)]
+            reqs = dist.batch_isend_irecv(ops_)
+        if not (is_causal and src > rank):
+            o_i, lse_i = attn_fn(q, k_cur, v_cur, tensor_layout=tensor_layout, is_causal=bool(is_causal and src == rank),
+                                 sm_scale=sm_scale, return_lse=True, **kwargs)
+            if o_acc is None:
+                o_acc, lse_acc = o_i.float(), lse_i
+            else:
+                o_acc, lse_acc = merge_attention_states(o_acc, lse_acc, o_i, lse_i, hnd)
+        for r in reqs:
+            r.wait()
+        if step + 1 < world:
+            k_cur, v_cur = k_nxt, v_nxt
+    return o_acc.to(q.dtype)

@@ -90,3 +90,50 @@ def test_ulysses_head_parallel_gloo_world2():
     mp.spawn(_ulysses_worker, args=(world, port, ret), nprocs=world, join=True)
     for r in range(world):
         assert all(ret[r]), f"rank {r}: {ret[r]}"
+
+
+def _ring_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sageattention_b200 import parallel
+    from oracle import sage_oracle as O
+    torch.manual_seed(0)
+    B, H, Hk, S, D = 1, 4, 2, 384, 64
+    q = torch.randn(B, H, S, D).half()
+    k = (torch.randn(B, Hk, S, D) + 2.0 * torch.randn(B, Hk, 1, D)).half()
+    v = torch.randn(B, Hk, S, D).half()
+    Sl = S // world
+    sl = slice(rank * Sl, (rank + 1) * Sl)
+    oks = []
+    for layout, causal in (("HND", False), ("HND", True), ("NHD", True)):
+        exact = O.sdpa_fp32(q, k, v, is_causal=causal)[:, :, sl]
+        single = O.sageattn_qk_int8_pv_fp8_cuda(q, k, v, is_causal=causal)[:, :, sl].float()
+        ql, kl, vl = q[:, :, sl], k[:, :, sl], v[:, :, sl]
+        if layout == "NHD":
+            ql, kl, vl = (t.transpose(1, 2).contiguous() for t in (ql, kl, vl))
+        o = parallel.sageattn_ring(ql, kl, vl, tensor_layout=layout, is_causal=causal, attn_fn=O.sageattn_qk_int8_pv_fp8_cuda)
+        if layout == "NHD":
+            o = o.transpose(1, 2)
+        err_ring, err_single = (o.float() - exact).abs().max().item(), (single - exact).abs().max().item()
+        # as accurate as the unsharded quantised call (per-slice smoothing / scales), far from "wrong merge" territory
+        oks.append(err_ring < max(2.0 * err_single, 2e-2))
+    # merge identity: two halves of the keys merged == attention over all keys (fp32 reference)
+    s_ = (q.float() @ k.float().repeat_interleave(2, 1).transpose(-1, -2)) * D ** -0.5
+    vf = v.float().repeat_interleave(2, 1)
+    h = S // 2
+    oa, ob = torch.softmax(s_[..., :h], -1) @ vf[:, :, :h], torch.softmax(s_[..., h:], -1) @ vf[:, :, h:]
+    om, lm = parallel.merge_attention_states(oa, torch.logsumexp(s_[..., :h], -1), ob, torch.logsumexp(s_[..., h:], -1))
+    oks.append((om - torch.softmax(s_, -1) @ vf).abs().max().item() < 1e-5 and (lm - torch.logsumexp(s_, -1)).abs().max().item() < 1e-5)
+    ret[rank] = tuple(oks)
+    dist.destroy_process_group()
+
+
+def test_ring_attention_gloo_world2():
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ring_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert all(ret[r]), f"rank {r}: {ret[r]}"
