@@ -222,7 +222,7 @@ def _expand_k_scale(k_scale, gran, Sk, BLKK=64):
 
 def attn_int8_fp8_cuda(q8, k8, v8, q_scale, k_scale, v_scale, *, qk_quant_gran="per_thread",
                        k_quant_gran=None, is_causal=False, sm_scale=1.0, pv_accum_dtype="fp32+fp32",
-                       out_dtype=torch.float16, kv_tile=64, return_lse=False, log2e=LOG2E_CU):
+                       out_dtype=torch.float16, kv_tile=64, return_lse=False, log2e=LOG2E_CU, exp2_fn=None):
     """csrc/qattn/qk_int_sv_f8_cuda_sm89.cuh:44-704 restated on [B,H,S,D] tensors.
 
     q8/k8 int8 [B,Hq|Hkv,S,D]; v8 fp8-e4m3 LOGICAL [B,Hkv,Skv,D]; scales packed as the reference.
@@ -234,7 +234,9 @@ def attn_int8_fp8_cuda(q8, k8, v8, q_scale, k_scale, v_scale, *, qk_quant_gran="
       P8    = e4m3_rn_satfinite(P)                                           (:478-493)
       O     = O*alpha + P8 @ V8   (fp32, or f16 per-tile accumulate)         (:896-974)
     epilogue: O/d * v_scale -> out_dtype;  lse = log2(d) + m                  (…sm89.cuh:572-703)
-    Causal uses top-left alignment (kv_idx > q_idx masked)."""
+    Causal uses top-left alignment (kv_idx > q_idx masked).
+    `exp2_fn` (default torch.exp2) replaces the exponential of P only — used by tests/test_poly_exp_numerics.py to
+    quantify the opt-in FMA-pipe polynomial of the sm_100a kernel (csrc/ptx.cuh ex2_poly2) against this restatement."""
     B, Hq, Sq, D = q8.shape
     _, Hk, Sk, _ = k8.shape
     g = Hq // Hk
@@ -264,7 +266,7 @@ def attn_int8_fp8_cuda(q8, k8, v8, q_scale, k_scale, v_scale, *, qk_quant_gran="
             S = torch.where(kj > qi, torch.tensor(MASK_VALUE), S)
         m_new = torch.maximum(m, S.amax(dim=-1) - S_FP8_OFFSET)
         alpha = torch.exp2(m - m_new)
-        P = torch.exp2(S - m_new[..., None])
+        P = (exp2_fn or torch.exp2)(S - m_new[..., None])
         d = d * alpha + P.sum(dim=-1)
         P8 = P.to(torch.float8_e4m3fn).float()
         Vt = vf[:, :, s0:s1]
@@ -365,7 +367,7 @@ def _pad_head_dim(q, k, v):
 def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout="HND", is_causal=False,
                                  qk_quant_gran="per_thread", sm_scale=None,
                                  pv_accum_dtype="fp32+fp16", smooth_k=True, smooth_v=False,
-                                 return_lse=False, kv_tile=64, emulate_f16_accum=True):
+                                 return_lse=False, kv_tile=64, emulate_f16_accum=True, exp2_fn=None):
     """sageattention/core.py:636-826 end to end (CPU).  emulate_f16_accum=False keeps the reference's V range
     for "fp32+fp16" (2.25) but accumulates PV in fp32 — the B200 kernel's arithmetic (tcgen05 f32 accumulation)."""
     dtype = q.dtype
@@ -390,7 +392,7 @@ def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout="HND", is_causal=False,
     o = attn_int8_fp8_cuda(_to_hnd(q8, tensor_layout), _to_hnd(k8, tensor_layout), v8, qs, ks, vs,
                            qk_quant_gran=qk_quant_gran, is_causal=is_causal, sm_scale=sm_scale,
                            pv_accum_dtype=pv_accum_dtype if emulate_f16_accum else "fp32+fp32", out_dtype=dtype,
-                           kv_tile=kv_tile, return_lse=return_lse)
+                           kv_tile=kv_tile, return_lse=return_lse, exp2_fn=exp2_fn)
     lse = None
     if return_lse:
         o, lse = o

@@ -16,28 +16,32 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 EXTRA_FLAGS = {}
 
 
-def _digest():
+def _digest(extra=()):
     h = hashlib.sha256()
     for f in SOURCES + HEADERS:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(fh.read())
-    h.update((" ".join(NVCC_FLAGS) + repr(sorted(EXTRA_FLAGS.items()))).encode())
+    h.update((" ".join(NVCC_FLAGS) + repr(sorted(EXTRA_FLAGS.items())) + " ".join(extra)).encode())
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), variant: str = "") -> str:
+    """Default: the product library.  `variant` + `defines` build an experiment next to it
+    (lib/libsab_<variant>.so with -D<define>...; select it at run time with SAB_LIB_PATH) — the product .so is untouched."""
+    LIB = globals()["LIB"] if not variant else os.path.join(HERE, "lib", f"libsab_{variant}.so")
+    extra = [f"-D{d}" for d in defines]
     stamp = LIB + ".sha256"
-    dig = _digest()
+    dig = _digest(extra)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    objdir = os.path.join(os.path.dirname(LIB), "obj")
+    objdir = os.path.join(os.path.dirname(LIB), "obj" + ("_" + variant if variant else ""))
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        cmd = [nvcc] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
         return src, obj, subprocess.run(cmd, capture_output=True, text=True)
 
     from concurrent.futures import ThreadPoolExecutor
@@ -54,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(log)
     if failed or link.returncode != 0:
         raise RuntimeError("nvcc failed building libsageattn_b200.so (%s)" % (", ".join(failed) or "link"))
-    with open(os.path.join(os.path.dirname(LIB), "ptxas.log"), "w") as fh:
+    with open(os.path.join(os.path.dirname(LIB), "ptxas" + ("_" + variant if variant else "") + ".log"), "w") as fh:
         fh.write(log)
     with open(stamp, "w") as fh:
         fh.write(dig)
@@ -62,4 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    # python -m sageattention_b200.build [--force] [--variant NAME -DFOO=1 -DBAR ...]
+    argv = sys.argv[1:]
+    name = argv[argv.index("--variant") + 1] if "--variant" in argv else ""
+    print(build(force="--force" in argv, verbose=True, defines=[a[2:] for a in argv if a.startswith("-D")], variant=name))

@@ -353,6 +353,14 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             unpack_f2(ffma2(f2, coef2[g], nm2), y0, y1);
 #ifdef SAB_EXP_NO_MUFU
             e[u] = y0 * 0.001f; e[u + 1] = y1 * 0.001f;
+#elif defined(SAB_POLY_EXP_PAIRS)
+            // opt-in build: SAB_POLY_EXP_PAIRS of every 4 column pairs take the polynomial on the FMA pipe (ptx.cuh)
+            if (((i >> 1) & 3) < SAB_POLY_EXP_PAIRS) {
+              ex2_poly2(y0, y1, e[u], e[u + 1]);
+            } else {
+              e[u] = ex2_approx(y0);
+              e[u + 1] = ex2_approx(y1);
+            }
 #else
             e[u] = ex2_approx(y0);
             e[u + 1] = ex2_approx(y1);

@@ -265,6 +265,28 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^y for a PAIR of arguments on the FMA / ALU pipes instead of the MUFU (opt-in builds, -DSAB_POLY_EXP_PAIRS=n; off by
+// default because P stops being bit-identical to the reference kernel's).  y is clamped to >= -126, split into
+// floor(y) + f with the round-down magic add (FADD.RM with 1.5*2^23 leaves floor(y) in the low mantissa bits, exactly),
+// 2^f on [0,1) is a degree-3 minimax polynomial with p(0) = 1 (max relative error 8.6e-5, coefficients fitted in
+// tests/test_poly_exp_numerics.py), and floor(y) is added to the exponent field with one shift-add.  6 packed FMA-pipe
+// instructions per pair + 2 FMNMX + 2 shift-adds, against 2 MUFU.EX2.
+__device__ __forceinline__ void ex2_poly2(float y0, float y1, float& e0, float& e1) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23 = 0x4B400000: low 9 bits zero, so (bits << 23) == floor(y) << 23
+  const uint64_t yy = pack_f2(fmaxf(y0, -126.f), fmaxf(y1, -126.f));
+  uint64_t r;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(yy), "l"(pack_f2(kMagic, kMagic)));
+  const uint64_t fl = fadd2(r, pack_f2(-kMagic, -kMagic));              // floor(y) as a float, exact
+  const uint64_t fr = ffma2(fl, pack_f2(-1.f, -1.f), yy);               // y - floor(y) in [0, 1]
+  uint64_t p = ffma2(fr, pack_f2(0.07706724107265472f, 0.07706724107265472f), pack_f2(0.22764497995376587f, 0.22764497995376587f));
+  p = ffma2(p, fr, pack_f2(0.6951166391372681f, 0.6951166391372681f));
+  p = ffma2(p, fr, pack_f2(1.f, 1.f));
+  float p0, p1, r0, r1;
+  unpack_f2(p, p0, p1);
+  unpack_f2(r, r0, r1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
 // Pack 2 fp32 -> f16x2 (round-nearest-even); low half = a.
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
   uint32_t r;

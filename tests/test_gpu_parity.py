@@ -256,11 +256,6 @@ def test_triton_path_shell_vs_reference_triton_fixtures(env, name):
     assert (o.float() - o_ref.float()).abs().max().item() <= 4e-3
 
 
-_MASK_GUARD = pytest.mark.skipif(os.environ.get("SAB_TEST_ATTN_MASK", "0") != "1",
-                                 reason="attn_mask kernel variant not yet validated on a B200 (set SAB_TEST_ATTN_MASK=1)")
-
-
-@_MASK_GUARD
 @pytest.mark.parametrize("name", ["attn_mask_bool_d64", "attn_mask_bias_d128"])
 def test_triton_path_attn_mask_vs_reference_triton_fixtures(env, name):
     """attn_mask of sageattn_qk_int8_pv_fp16_triton (core.py:248-250, 310-325; attn_qk_int8_per_block.py:33-52): bool mask
@@ -275,7 +270,6 @@ def test_triton_path_attn_mask_vs_reference_triton_fixtures(env, name):
     assert (o.float() - o_ref.float()).abs().max().item() <= 4e-3
 
 
-@_MASK_GUARD
 def test_triton_path_attn_mask_vs_oracle(env):
     """More mask shapes against the CPU oracle: NHD layout, bf16 bias, GQA, 2-D / per-batch broadcast masks, ragged lengths,
     qo_len != kv_len; plus the host-side contract (dtype / causal asserts, broadcast failure)."""

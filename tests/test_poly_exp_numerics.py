@@ -1,0 +1,101 @@
+"""CPU numerics of the opt-in FMA-pipe exponential of the sm_100a attention kernel (csrc/ptx.cuh `ex2_poly2`, builds with
+-DSAB_POLY_EXP_PAIRS=n): a float32 restatement of the instruction sequence, its error against exp2, and what replacing
+n of every 4 column pairs of P by it does to the attention output of the CPU oracle.  This is the evidence DESIGN.md §4.3
+quotes for "far inside the 1e-2 tolerance"; the default build does not use the polynomial."""
+import numpy as np
+import torch
+
+from oracle import sage_oracle as O
+
+C1, C2, C3 = np.float32(0.6951166391372681), np.float32(0.22764497995376587), np.float32(0.07706724107265472)
+MAGIC_BITS = 0x4B400000   # 1.5 * 2^23
+
+
+def _fma32(a, b, c):
+    """fp32 fused multiply-add: the product of two fp32 numbers and the sum are exact in float64 up to one rounding, which is
+    then rounded again to fp32 (double rounding can differ from a true FMA by 1 ulp in ~1e-9 of the cases: irrelevant here)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def ex2_poly_np(y):
+    """ex2_poly2 for one lane: clamp, floor via the round-down magic add, degree-3 Horner, exponent insertion."""
+    y = np.maximum(np.asarray(y, dtype=np.float32), np.float32(-126.0))
+    fl = np.floor(y).astype(np.float32)                      # add.rm(y, 1.5*2^23) - 1.5*2^23 == floor(y), exact
+    r_bits = (MAGIC_BITS + fl.astype(np.int64)).astype(np.int64)
+    fr = _fma32(fl, np.float32(-1.0) * np.ones_like(y), y)   # y - floor(y) in [0, 1]
+    p = _fma32(fr, C3 * np.ones_like(y), C2 * np.ones_like(y))
+    p = _fma32(p, fr, C1 * np.ones_like(y))
+    p = _fma32(p, fr, np.ones_like(y))
+    bits = (p.view(np.uint32).astype(np.int64) + ((r_bits << 23) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    return bits.astype(np.uint32).view(np.float32)
+
+
+def test_polynomial_is_the_minimax_fit_and_accurate():
+    y = np.concatenate([np.linspace(-126.0, 9.0, 2_000_001), -np.logspace(-9, 2, 100001), [0.0, -0.0, -1.0, 8.807, -1e-8]]).astype(np.float32)
+    got = ex2_poly_np(y).astype(np.float64)
+    ref = np.exp2(y.astype(np.float64))
+    rel = np.abs(got / ref - 1.0)
+    assert rel.max() <= 8.8e-5, rel.max()                   # fitted bound 8.56e-5 + fp32 evaluation
+    assert ex2_poly_np(np.float32(0.0)) == np.float32(1.0) and ex2_poly_np(np.float32(-3.0)) == np.float32(0.125)
+    assert np.all(np.diff(ex2_poly_np(np.sort(y))) >= -1e-4 * ex2_poly_np(np.sort(y))[1:])   # monotone up to the seam at integers
+    # arguments far below the clamp (masked sentinels) give 2^-126, not NaN / inf
+    assert ex2_poly_np(np.float32(-5e6)) == np.float32(2.0 ** -126)
+    # the coefficients are the minimax fit of 2^x / relative error on [0,1] with p(0) = 1 (refit, compare the bound)
+    from scipy.optimize import linprog
+    x = np.linspace(0, 1, 2001); f = 2.0 ** x
+    A = np.stack([x / f, x ** 2 / f, x ** 3 / f], 1); b = 1 - 1 / f
+    n = len(x)
+    r = linprog([0, 0, 0, 1], A_ub=np.block([[A, -np.ones((n, 1))], [-A, -np.ones((n, 1))]]), b_ub=np.concatenate([b, -b]),
+                bounds=[(None, None)] * 4)
+    assert r.status == 0 and abs(r.x[3] - 8.56e-5) < 2e-7
+    assert np.allclose(r.x[:3], [float(C1), float(C2), float(C3)], atol=2e-5)
+
+
+def _mixed_exp2(pairs):
+    """exp2 of a [.., 64]-wide tile where `pairs` of every 4 column pairs take the polynomial (attn.cu: ((i >> 1) & 3) < n)."""
+    def fn(t):
+        ref = torch.exp2(t)
+        poly = torch.from_numpy(ex2_poly_np(t.numpy()))
+        col = torch.arange(t.shape[-1])
+        use = ((col >> 1) & 3) < pairs
+        return torch.where(use, poly, ref)
+    return fn
+
+
+def test_effect_on_attention_output_is_far_inside_the_tolerance():
+    torch.manual_seed(0)
+    B, H, S, D = 1, 2, 512, 128
+    q, k, v = (torch.randn(B, H, S, D).to(torch.float16) for _ in range(3))      # fp16 output grid: 2^-10 relative
+    k = k + 3.0 * torch.randn(B, H, 1, D).to(torch.float16)
+    exact = O.sdpa_fp32(q, k, v)
+    worst = {}
+    for causal in (False, True):
+        base, base_lse = O.sageattn_qk_int8_pv_fp8_cuda(q, k, v, is_causal=causal, return_lse=True, emulate_f16_accum=False)
+        for pairs in (1, 2, 4):
+            o, lse = O.sageattn_qk_int8_pv_fp8_cuda(q, k, v, is_causal=causal, return_lse=True, emulate_f16_accum=False,
+                                                    exp2_fn=_mixed_exp2(pairs))
+            diff = (o.float() - base.float()).abs().max().item()
+            worst[(causal, pairs)] = diff
+            # the polynomial's 8.6e-5 relative error reaches O through d (sum of un-rounded P) and through the rare
+            # changed e4m3 rounding of a P element; one fp16 ulp of the largest outputs (|O| < 4) is 2e-3
+            assert diff <= 4e-3, (causal, pairs, diff)
+            assert (lse - base_lse).abs().max().item() <= 2e-4
+            if not causal:   # and the error against exact attention does not grow
+                e0 = (base.float() - exact.float()).abs().mean().item()
+                e1 = (o.float() - exact.float()).abs().mean().item()
+                assert e1 <= 1.02 * e0 + 1e-5, (pairs, e0, e1)
+    print("max |O_poly - O_mufu|:", worst)
+
+
+def test_e4m3_flip_rate_of_P():
+    """How often the polynomial changes the e4m3 rounding of P in (0, 448]: the relative error is 8.6e-5 against a rounding
+    interval of 2^-3 .. 2^-4 relative width, so about 0.1-0.3 % of the emulated elements move by one e4m3 ulp."""
+    g = np.random.default_rng(0)
+    y = (8.807 - g.exponential(3.0, size=1_000_000)).astype(np.float32)
+    a = torch.from_numpy(np.exp2(y.astype(np.float64)).astype(np.float32)).to(torch.float8_e4m3fn).float()
+    b = torch.from_numpy(ex2_poly_np(y)).to(torch.float8_e4m3fn).float()
+    flips = (a != b).float().mean().item()
+    assert flips < 5e-3, flips
+    rel = ((a - b).abs() / a.clamp_min(2.0 ** -9)).max().item()
+    assert rel <= 0.126, rel                                 # never more than one e4m3 step (2^-3 relative)
+    print("e4m3 flip rate:", flips)
