@@ -40,40 +40,62 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  nvidia-smi needs ~0.3 s before its first row and
+    the timed region of a short run lasts tens of milliseconds, so the sampler is started before the warm-up, every row is
+    stamped on arrival, and only rows that arrived inside a marked window (begin() .. end()) are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows, self._t0 = index, [], None, [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import shutil
+            pre = ["stdbuf", "-oL"] if shutil.which("stdbuf") else []
+            self.proc = subprocess.Popen(pre + ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                                "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
             self.proc = None
 
     def _read(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            try:      # nvidia-smi's own sample time (robust against pipe buffering); arrival time if it does not parse
+                t = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                t = time.time()
+            self.rows.append((t, r))
+
+    def begin(self):
+        self._t0 = time.time()
+
+    def end(self):
+        if self._t0 is not None:
+            self.windows.append((self._t0, time.time()))
+            self._t0 = None
+
+    def n_in_windows(self):
+        return sum(1 for t, r in self.rows if any(a <= t <= b for a, b in self.windows) and len(r) >= 8)
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        self.t.join(timeout=2.0)
+        rows = [r for t, r in self.rows if any(a <= t <= b for a, b in self.windows) and len(r) >= 8]
+        sm = sorted(int(float(r[1])) for r in rows if r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window_s": round(sum(b - a for a, b in self.windows), 3)}
 
 
 def flops(B, H, Sq, Sk, D, causal=False):
@@ -175,26 +197,41 @@ def run_ours(args):
         launches_per_step = 9
         scaling = "strong"
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here so that it is streaming by the time the timed region begins)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         o = step()
     torch.cuda.synchronize()
 
     # ---- value: device-resident inputs (each of q,k,v is >= 2x the 126 MB L2 at N=1: no flush needed)
-    sampler = ClockSampler(local) if rank == 0 else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     if sampler:
-        sampler.start()
+        sampler.begin()
     ms = time_events(step, args.steps)
+    if sampler:
+        sampler.end()
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
     ms = float(t.item())
-    clocks = sampler.stop() if sampler else None
     value = total_flops / (ms * 1e-3) / 1e12
+    # a K-step timed region can be shorter than the sampler's period: keep the same step running (untimed, all ranks, same
+    # count so the collectives match) until the window holds a few samples of the clocks under this load
+    extra = max(args.steps, int(0.5 / max(ms * 1e-3, 1e-6))) if (ms * args.steps < 400.0) else 0
+    if extra:
+        if sampler:
+            sampler.begin()
+        for _ in range(extra):
+            step()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.end()
+    clocks = sampler.stop() if sampler else None
 
     out = None
     cached_kv = None
