@@ -246,6 +246,13 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     long long* tl = reinterpret_cast<long long*>(p.dbg) + 4096;
 #endif
 
+#ifdef SAB_PREMAX
+    // opt-in build (-DSAB_PREMAX=8|16): the integer row maxima of S(j+1) are gathered in 8/16-column chunks INSIDE the exponential
+    // loop of tile j (issue slots that otherwise wait for the MUFU), so the serial max -> alpha chain of tile j+1 starts
+    // from 4 integers instead of 64.  Only for mask-free tiles whose S buffer is already complete (non-blocking check).
+    int pm[4] = {kIntSentinel, kIntSentinel, kIntSentinel, kIntSentinel};   // kKT: per scale group; else 4 partial chains
+    bool have_pre = false;
+#endif
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t tS = tmem_base + lane_off + (j & 1) * BN;
       // dequant coefficient per scale group of this tile (…sm89.cuh:116-132, 255-257); tile j == 64-key block j
@@ -258,8 +265,13 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && (j + 1) * BN > p.causal_q_offset + qt * BM + 1);
 
       SAB_TL(0);
-      mbar_wait_wd(s_full + (j & 1), s_parity(j));
-      tc_fence_after();
+#ifdef SAB_PREMAX
+      if (!have_pre)   // otherwise the pre-max pass of the previous iteration saw s_full(j) complete (and fenced)
+#endif
+      {
+        mbar_wait_wd(s_full + (j & 1), s_parity(j));
+        tc_fence_after();
+      }
       SAB_TL(1);
       uint32_t s[BN];
       {
@@ -288,8 +300,9 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
 
-      auto tile = [&](auto masked_tag) {
+      auto tile = [&](auto masked_tag, [[maybe_unused]] auto pre_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
+        [[maybe_unused]] constexpr bool PRE = decltype(pre_tag)::value;   // SAB_PREMAX builds: gather the maxima of S(j+1) in this tile
         // ---- row max.  Scales are positive, so max_c(S_c*coef_g(c)) = max_g(coef_g * max_{c in g} S_c): integer
         //      max per scale group (DPX 3-input max), one int->float conversion per group instead of per element.
         if constexpr (MASKED) {
@@ -298,9 +311,17 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (i >= limit) s[i] = uint32_t(kIntSentinel);
         }
         float mx = kMaskValue;
+#ifdef SAB_PREMAX
+        const bool use_pre = !MASKED && have_pre;
+#endif
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           int v = kIntSentinel;
+#ifdef SAB_PREMAX
+          if (use_pre) {
+            v = kKT ? pm[g] : max(max(pm[0], pm[1]), max(pm[2], pm[3]));
+          } else
+#endif
           if constexpr (kKT) {
 #pragma unroll
             for (int i8 = 0; i8 < BN; i8 += 8) v = __vimax3_s32(v, int(s[i8 + 2 * g]), int(s[i8 + 2 * g + 1]));
@@ -341,9 +362,21 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint64_t nm2 = pack_f2(nm, nm);
         uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
         uint32_t pk[PCOLS];
+#ifdef SAB_PREMAX
+        constexpr int PMW = SAB_PREMAX / 4;   // exp-loop iterations (4 elements each) per pre-max chunk
+        static_assert(SAB_PREMAX == 8 || SAB_PREMAX == 16, "SAB_PREMAX: chunk width 8 or 16 columns");
+        [[maybe_unused]] uint32_t nxt[SAB_PREMAX];
+        [[maybe_unused]] const uint32_t tN = tmem_base + lane_off + ((j + 1) & 1) * BN;
+        if constexpr (PRE) pm[0] = pm[1] = pm[2] = pm[3] = kIntSentinel;   // (the maxima of tile j were consumed above)
+#endif
 #pragma unroll
         for (int w = 0; w < BN / 4; ++w) {
           float e[4];
+#ifdef SAB_PREMAX
+          if constexpr (PRE) {
+            if ((w % PMW) == 0) tmem_ld_chunk(tN + 4 * w, nxt);            // a chunk of S(j+1), in flight under the exps
+          }
+#endif
 #pragma unroll
           for (int u = 0; u < 4; u += 2) {
             const int i = 4 * w + u;
@@ -380,7 +413,22 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           } else {
             pk[w] = pack_e4m3x4(e[0], e[1], e[2], e[3]);
           }
+#ifdef SAB_PREMAX
+          if constexpr (PRE) {
+            if ((w % PMW) == PMW - 1) {   // the chunk issued 8 / 16 exponentials ago has landed: fold it into the maxima
+              tc_wait_ld();
+#pragma unroll
+              for (int k8 = 0; k8 < SAB_PREMAX; k8 += 8) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) pm[g] = __vimax3_s32(pm[g], int(nxt[k8 + 2 * g]), int(nxt[k8 + 2 * g + 1]));
+              }
+            }
+          }
+#endif
         }
+#ifdef SAB_PREMAX
+        have_pre = PRE;
+#endif
         {
           float a0, a1, a2, a3;
           unpack_f2(fadd2(acc[0], acc[1]), a0, a1);
@@ -428,9 +476,26 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tmem_st32(tS, pk);
         }
       };
+#ifdef SAB_PREMAX
+      // decide before the tile starts (non-blocking): is S(j+1) complete and mask-free?  Warp-uniform by the vote — the
+      // tcgen05.ld of the chunks is .sync.aligned.  The exp loop of the PRE instantiation is branch-free.
+      bool pre_ok = false;
+      if constexpr (!kMask) {
+        const bool next_masked = (j + 1 >= n_kv) || (kv_len - (j + 1) * BN < BN) ||
+                                 (p.causal && (j + 2) * BN > p.causal_q_offset + qt * BM + 1);
+        if (!masked_tile && !next_masked)
+          pre_ok = __all_sync(0xffffffffu, mbar_test_wait(s_full + ((j + 1) & 1), s_parity(j + 1)));
+        if (pre_ok) tc_fence_after();
+      }
       if (kMask && p.mask_kind == 2) tile_bias();
-      else if (kMask || masked_tile) tile(std::true_type{});
-      else tile(std::false_type{});
+      else if (kMask || masked_tile) tile(std::true_type{}, std::false_type{});
+      else if (pre_ok) tile(std::false_type{}, std::true_type{});
+      else tile(std::false_type{}, std::false_type{});
+#else
+      if (kMask && p.mask_kind == 2) tile_bias();
+      else if (kMask || masked_tile) tile(std::true_type{}, std::false_type{});
+      else tile(std::false_type{}, std::false_type{});
+#endif
 
       SAB_TL(5);
       tc_wait_st();

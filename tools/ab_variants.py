@@ -1,0 +1,66 @@
+"""A/B harness for opt-in kernel experiments (compile-time variants of csrc/attn.cu next to the product library).
+
+  python tools/ab_variants.py build            # here (CPU box): nvcc every variant into sageattention_b200/lib/libsab_<name>.so
+  python tools/ab_variants.py run [names...]   # on the GPU box: for the product library and each variant, the attention
+                                               # parity tests + kernel-only timing (tools/perf_kernel.py), each in its own
+                                               # subprocess under a timeout (a hanging variant costs 120 s, not the box)
+
+The product library is never replaced: a variant is selected per process with SAB_LIB_PATH (sageattention_b200/_capi.py).
+Variants whose P is not bit-identical to the reference kernel (polynomial exp2) run the parity tests with the tolerance
+tests already state against the oracle (5e-3); the bit-exactness tests of S / P / m / d are expected to fail for them and
+are excluded by -k."""
+import os, subprocess, sys, time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+VARIANTS = {
+    # name: (defines, what it changes)
+    "poly1": (["SAB_POLY_EXP_PAIRS=1"], "25 % of the exponentials as a degree-3 polynomial on the FMA pipe (ptx.cuh ex2_poly2)"),
+    "poly2": (["SAB_POLY_EXP_PAIRS=2"], "50 % of the exponentials on the FMA pipe"),
+    "premax8": (["SAB_PREMAX=8"], "row maxima of S(j+1) gathered inside the exp loop of tile j (8-column chunks)"),
+    "premax8_poly1": (["SAB_PREMAX=8", "SAB_POLY_EXP_PAIRS=1"], "both"),
+}
+PARITY_K = "attention_vs_oracle or full_size_config1 or api_behaviour"
+
+
+def build():
+    from sageattention_b200 import build as b
+    for name, (defs, what) in VARIANTS.items():
+        t0 = time.time()
+        lib = b.build(variant=name, defines=defs)
+        print(f"[build] {name:16s} {time.time() - t0:5.1f} s  {lib}  ({what})", flush=True)
+
+
+def run(names):
+    libdir = os.path.join(ROOT, "sageattention_b200", "lib")
+    todo = [("product", None)] + [(n, os.path.join(libdir, f"libsab_{n}.so")) for n in (names or VARIANTS)]
+    for name, lib in todo:
+        if lib is not None and not os.path.exists(lib):
+            print(f"== {name}: {lib} not built (python tools/ab_variants.py build)", flush=True)
+            continue
+        env = dict(os.environ)
+        if lib:
+            env["SAB_LIB_PATH"] = lib
+        print(f"== {name}", flush=True)
+        for what, cmd, tmo in (("parity", [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
+                                            "-k", PARITY_K, "-p", "no:cacheprovider"], 180),
+                               ("perf", [sys.executable, os.path.join(ROOT, "tools", "perf_kernel.py")], 120)):
+            try:
+                r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=tmo)
+                tail = (r.stdout.strip().splitlines() or [""])[-1]
+                print(f"   {what:6s} rc={r.returncode}: {tail}", flush=True)
+                if r.returncode != 0:
+                    print("   " + "\n   ".join((r.stdout + r.stderr).strip().splitlines()[-12:]), flush=True)
+            except subprocess.TimeoutExpired:
+                print(f"   {what:6s} TIMEOUT after {tmo} s (variant hangs?)", flush=True)
+                break
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "build":
+        build()
+    elif len(sys.argv) > 1 and sys.argv[1] == "run":
+        run(sys.argv[2:])
+    else:
+        print(__doc__)
