@@ -231,7 +231,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         if sampler:
             sampler.end()
-    clocks = sampler.stop() if sampler else None
+    try:
+        clocks = sampler.stop() if sampler else None
+    except Exception as e:      # the clocks line must never take the benchmark down
+        clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"sampler error: {e}"]}
 
     out = None
     cached_kv = None

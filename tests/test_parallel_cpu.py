@@ -39,9 +39,9 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_sp_host_logic_gloo_world2():
-    world = 2
-    port = 29500 + (os.getpid() % 2000)
+@pytest.mark.parametrize("world", [2, 4])
+def test_sp_host_logic_gloo_world2(world):
+    port = 29500 + (os.getpid() % 2000) + world
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
