@@ -281,6 +281,16 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld32(tS + 32, hi);
         tc_wait_ld();
       }
+#ifdef SAB_DEFER_PST
+      // opt-in build: the hand-off of P(j-1) (wait::st + fence + arrive, ~130 cycles of the serial chain) is taken here,
+      // after S(j) was waited for and loaded — the store issued at the end of the previous iteration has long landed.
+      // No cycle: s_full(j) depends on p_full(j-2), which was signalled one iteration earlier.
+      if (j > 0) {
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(p_full + ((j - 1) & 1));
+      }
+#endif
       SAB_TL(2);
       if (dump && j == 0) {
 #pragma unroll
@@ -498,10 +508,15 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #endif
 
       SAB_TL(5);
-      tc_wait_st();
-      SAB_TL(6);
-      tc_fence_before();
-      mbar_arrive(p_full + (j & 1));
+#ifdef SAB_DEFER_PST
+      if (j == n_kv - 1)   // last tile: nothing to hide the hand-off under
+#endif
+      {
+        tc_wait_st();
+        SAB_TL(6);
+        tc_fence_before();
+        mbar_arrive(p_full + (j & 1));
+      }
       SAB_TL(7);
     }
 

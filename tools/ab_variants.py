@@ -19,7 +19,9 @@ VARIANTS = {
     "poly1": (["SAB_POLY_EXP_PAIRS=1"], "25 % of the exponentials as a degree-3 polynomial on the FMA pipe (ptx.cuh ex2_poly2)"),
     "poly2": (["SAB_POLY_EXP_PAIRS=2"], "50 % of the exponentials on the FMA pipe"),
     "premax8": (["SAB_PREMAX=8"], "row maxima of S(j+1) gathered inside the exp loop of tile j (8-column chunks)"),
-    "premax8_poly1": (["SAB_PREMAX=8", "SAB_POLY_EXP_PAIRS=1"], "both"),
+    "defer": (["SAB_DEFER_PST"], "hand-off of P(j-1) (wait::st + fence + arrive) taken after S(j) was loaded, off the serial chain"),
+    "defer_premax8": (["SAB_DEFER_PST", "SAB_PREMAX=8"], "both chain shorteners"),
+    "defer_premax8_poly1": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_POLY_EXP_PAIRS=1"], "chain shorteners + 25 % polynomial exp2"),
 }
 PARITY_K = "attention_vs_oracle or full_size_config1 or api_behaviour"
 
