@@ -357,8 +357,10 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         m = m_new;
         // publish alpha: the correction warpgroup rescales this row of O (in TMEM) concurrently with the exponentials.
         // Double-buffered: alpha(j+2) is written only after s_full(j+2), i.e. after the correction warp read alpha(j).
+#ifndef SAB_LATE_ALPHA
         s_alpha[(j & 1) * BM + row] = alpha;
         mbar_arrive(a_full + (j & 1));
+#endif
         const float nm = -m_new;
         SAB_TL(3);
 
@@ -417,6 +419,15 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             acc[(w & 1) * 2 + (u >> 1)] = fadd2(acc[(w & 1) * 2 + (u >> 1)], pack_f2(e[u], e[u + 1]));
           }
+#ifdef SAB_LATE_ALPHA
+          // opt-in build: alpha = ex2(m - m_new) comes off the MUFU queue behind the other CTA's exponentials; publishing it
+          // (STS + arrive) before the exp loop stalls this in-order warp for that latency.  The correction warps need it
+          // only before PV(j), so it is published after the first 8 exponentials of the tile were issued.
+          if (w == 1) {
+            s_alpha[(j & 1) * BM + row] = alpha;
+            mbar_arrive(a_full + (j & 1));
+          }
+#endif
           if constexpr (kPV16) {
             pk[2 * w] = pack_f16x2(e[0], e[1]);       // p.to(tl.float16), attn_qk_int8_per_block.py:62
             pk[2 * w + 1] = pack_f16x2(e[2], e[3]);

@@ -20,6 +20,8 @@ VARIANTS = {
     "poly2": (["SAB_POLY_EXP_PAIRS=2"], "50 % of the exponentials on the FMA pipe"),
     "premax8": (["SAB_PREMAX=8"], "row maxima of S(j+1) gathered inside the exp loop of tile j (8-column chunks)"),
     "defer": (["SAB_DEFER_PST"], "hand-off of P(j-1) (wait::st + fence + arrive) taken after S(j) was loaded, off the serial chain"),
+    "late_alpha": (["SAB_LATE_ALPHA"], "alpha published after the first 8 exponentials of the tile instead of before the loop"),
+    "all_chain": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_LATE_ALPHA"], "the three chain shorteners together (P stays bit-identical)"),
     "defer_premax8": (["SAB_DEFER_PST", "SAB_PREMAX=8"], "both chain shorteners"),
     "defer_premax8_poly1": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_POLY_EXP_PAIRS=1"], "chain shorteners + 25 % polynomial exp2"),
 }
