@@ -222,7 +222,7 @@ def _expand_k_scale(k_scale, gran, Sk, BLKK=64):
 
 def attn_int8_fp8_cuda(q8, k8, v8, q_scale, k_scale, v_scale, *, qk_quant_gran="per_thread",
                        k_quant_gran=None, is_causal=False, sm_scale=1.0, pv_accum_dtype="fp32+fp32",
-                       out_dtype=torch.float16, kv_tile=64, return_lse=False, log2e=LOG2E_CU, exp2_fn=None):
+                       out_dtype=torch.float16, kv_tile=64, return_lse=False, log2e=LOG2E_CU, exp2_fn=None, lazy_tau=None):
     """csrc/qattn/qk_int_sv_f8_cuda_sm89.cuh:44-704 restated on [B,H,S,D] tensors.
 
     q8/k8 int8 [B,Hq|Hkv,S,D]; v8 fp8-e4m3 LOGICAL [B,Hkv,Skv,D]; scales packed as the reference.
@@ -236,7 +236,9 @@ def attn_int8_fp8_cuda(q8, k8, v8, q_scale, k_scale, v_scale, *, qk_quant_gran="
     epilogue: O/d * v_scale -> out_dtype;  lse = log2(d) + m                  (…sm89.cuh:572-703)
     Causal uses top-left alignment (kv_idx > q_idx masked).
     `exp2_fn` (default torch.exp2) replaces the exponential of P only — used by tests/test_poly_exp_numerics.py to
-    quantify the opt-in FMA-pipe polynomial of the sm_100a kernel (csrc/ptx.cuh ex2_poly2) against this restatement."""
+    quantify the opt-in FMA-pipe polynomial of the sm_100a kernel (csrc/ptx.cuh ex2_poly2) against this restatement.
+    `lazy_tau` (default None = the reference rule) restates the opt-in -DSAB_LAZY_RESCALE=tau build of the sm_100a kernel: the
+    running max only moves when it grew by more than tau (log2 units) and the exponent offset is 8.807 - tau."""
     B, Hq, Sq, D = q8.shape
     _, Hk, Sk, _ = k8.shape
     g = Hq // Hk
@@ -264,7 +266,11 @@ def attn_int8_fp8_cuda(q8, k8, v8, q_scale, k_scale, v_scale, *, qk_quant_gran="
         if is_causal:
             kj = torch.arange(s0, s1)[None, :]
             S = torch.where(kj > qi, torch.tensor(MASK_VALUE), S)
-        m_new = torch.maximum(m, S.amax(dim=-1) - S_FP8_OFFSET)
+        if lazy_tau is None:
+            m_new = torch.maximum(m, S.amax(dim=-1) - S_FP8_OFFSET)
+        else:
+            m_true = torch.maximum(m, S.amax(dim=-1) - (S_FP8_OFFSET - float(lazy_tau)))
+            m_new = torch.where(m_true - m > float(lazy_tau), m_true, m)
         alpha = torch.exp2(m - m_new)
         P = (exp2_fn or torch.exp2)(S - m_new[..., None])
         d = d * alpha + P.sum(dim=-1)
@@ -367,7 +373,7 @@ def _pad_head_dim(q, k, v):
 def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout="HND", is_causal=False,
                                  qk_quant_gran="per_thread", sm_scale=None,
                                  pv_accum_dtype="fp32+fp16", smooth_k=True, smooth_v=False,
-                                 return_lse=False, kv_tile=64, emulate_f16_accum=True, exp2_fn=None):
+                                 return_lse=False, kv_tile=64, emulate_f16_accum=True, exp2_fn=None, lazy_tau=None):
     """sageattention/core.py:636-826 end to end (CPU).  emulate_f16_accum=False keeps the reference's V range
     for "fp32+fp16" (2.25) but accumulates PV in fp32 — the B200 kernel's arithmetic (tcgen05 f32 accumulation)."""
     dtype = q.dtype
@@ -392,7 +398,7 @@ def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout="HND", is_causal=False,
     o = attn_int8_fp8_cuda(_to_hnd(q8, tensor_layout), _to_hnd(k8, tensor_layout), v8, qs, ks, vs,
                            qk_quant_gran=qk_quant_gran, is_causal=is_causal, sm_scale=sm_scale,
                            pv_accum_dtype=pv_accum_dtype if emulate_f16_accum else "fp32+fp32", out_dtype=dtype,
-                           kv_tile=kv_tile, return_lse=return_lse, exp2_fn=exp2_fn)
+                           kv_tile=kv_tile, return_lse=return_lse, exp2_fn=exp2_fn, lazy_tau=lazy_tau)
     lse = None
     if return_lse:
         o, lse = o

@@ -351,7 +351,18 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mx = fmaxf(mx, c);
         }
         // fp8 P: update_mdo with the -log2(448) offset (attn_utils.cuh:377-396); fp16 P: plain running max (Triton path)
+#ifdef SAB_LAZY_RESCALE
+        // opt-in build (-DSAB_LAZY_RESCALE=tau, log2 units): the running max is only moved when it grew by more than tau;
+        // otherwise P(j) is taken against the stale max (alpha == 1, no O rescale).  The exponent offset shrinks by tau so
+        // that P still fits (0, 448]; e4m3 is a floating format, so P keeps the reference's mantissa bits with a shifted
+        // exponent (elements below 2^(tau-18) of the row maximum flush to zero instead of 2^-18), and d, O and the LSE stay
+        // consistent because they are all relative to the max in use.  With 32 rows per warp and ~1/j chance of a new row
+        // maximum at tile j, the exact rule rescales in ~60 % of the tiles at S=8192; a jump of more than 2^tau is rare.
+        const float m_true = fmaxf(m, kPV16 ? mx : mx - (kFp8Offset - float(SAB_LAZY_RESCALE)));
+        const float m_new = (m_true - m > float(SAB_LAZY_RESCALE)) ? m_true : m;
+#else
         const float m_new = fmaxf(m, kPV16 ? mx : mx - kFp8Offset);
+#endif
         const float alpha = ex2_approx(m - m_new);
         d *= alpha;
         m = m_new;
