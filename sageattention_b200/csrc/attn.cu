@@ -662,11 +662,11 @@ static bool use_hd64_kernel() {
 // SAB_ATTN_KERNEL=single|pair selects the kernel.  Default: single (one Q tile per CTA, two CTAs per SM) — measured
 // faster on B200 (1.28 vs 1.06 PFLOP/s at hd128 S=8192); pair (attn_pair.cu: two Q tiles per CTA, exp ping-pong) is kept
 // as an experiment: with one warp per scheduler in the exp phase it is latency-bound.
-static int attn_kernel_mode() {   // 0 single, 1 pair, 2 split (attn_split.cu: two softmax threads per row)
+static int attn_kernel_mode() {   // 0 single, 1 pair, 2 split (attn_split.cu: two softmax threads per row), 3 alt (attn_alt.cu)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SAB_ATTN_KERNEL");
-    v = (e == nullptr) ? 0 : (e[0] == 'p' ? 1 : (e[0] == 's' && e[1] == 'p' ? 2 : 0));
+    v = (e == nullptr) ? 0 : (e[0] == 'p' ? 1 : (e[0] == 's' && e[1] == 'p' ? 2 : (e[0] == 'a' ? 3 : 0)));
   }
   return v;
 }
@@ -677,6 +677,11 @@ template <int D, bool kKT, typename OutT>
 int launch_attn_split(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                       cudaStream_t stream);
 
+// attn_alt.cu (experiment, hd128 only): two softmax warpgroups on alternate key tiles
+template <int D, bool kKT, typename OutT>
+int launch_attn_alt(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                    cudaStream_t stream);
+
 template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
@@ -686,6 +691,9 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   }
   if constexpr (!kPV16) {
     if (attn_kernel_mode() == 2 && p.dbg == nullptr) return launch_attn_split<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
+  }
+  if constexpr (D == 128 && !kPV16) {
+    if (attn_kernel_mode() == 3 && p.dbg == nullptr) return launch_attn_alt<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
   }
   if constexpr (D == 64 && !kPV16) {
     if (use_hd64_kernel() && p.dbg == nullptr) return launch_attn_hd64<kKT, OutT>(tq, tk, tv, p, grid, stream);

@@ -27,6 +27,17 @@ VARIANTS = {
     "defer_premax8": (["SAB_DEFER_PST", "SAB_PREMAX=8"], "both chain shorteners"),
     "defer_premax8_poly1": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_POLY_EXP_PAIRS=1"], "chain shorteners + 25 % polynomial exp2"),
 }
+# attn_alt.cu (two softmax warpgroups on alternate key tiles) is selected at run time, on any library
+ENVS = {
+    "alt": {"SAB_ATTN_KERNEL": "alt"},
+    "alt_tau3": {"SAB_ATTN_KERNEL": "alt"},
+    "alt_tau3_poly1": {"SAB_ATTN_KERNEL": "alt"},
+}
+VARIANTS.update({
+    "alt": ([], "attn_alt.cu with the exact max rule (in-line O rescale in most tiles)"),
+    "alt_tau3": (["SAB_ALT_TAU=3"], "attn_alt.cu with the lazy max (tau = 3)"),
+    "alt_tau3_poly1": (["SAB_ALT_TAU=3", "SAB_POLY_EXP_PAIRS=1"], "attn_alt.cu, lazy max, 25 % polynomial exp2"),
+})
 PARITY_K = "attention_vs_oracle or full_size_config1 or api_behaviour"
 
 
@@ -34,6 +45,8 @@ def build():
     from sageattention_b200 import build as b
     for name, (defs, what) in VARIANTS.items():
         t0 = time.time()
+        if not defs:      # run-time variant of the product library: build it as a variant all the same (one path in run())
+            defs = ["SAB_VARIANT_TAG=1"]
         lib = b.build(variant=name, defines=defs)
         print(f"[build] {name:16s} {time.time() - t0:5.1f} s  {lib}  ({what})", flush=True)
 
@@ -48,6 +61,7 @@ def run(names):
         env = dict(os.environ)
         if lib:
             env["SAB_LIB_PATH"] = lib
+        env.update(ENVS.get(name, {}))
         print(f"== {name}", flush=True)
         for what, cmd, tmo in (("parity", [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
                                             "-k", PARITY_K, "-p", "no:cacheprovider"], 180),
