@@ -104,7 +104,6 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  auto s_parity = [](int t) { return uint32_t(t >> 1) & 1u; };
 
   if (warp >= 8) {
     setmaxnreg_dec_48();
@@ -193,6 +192,18 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float* ks_base = p.k_scale + (varlen ? int64_t(hk) : (int64_t(b) * p.Hkv + hk) * p.ks_stride_bh);
     const float qss = qs_base[int64_t(q_idx) * p.qs_stride_idx] * p.sm_scale_log2;
 
+    // Parity waits on the two s_full barriers (completion c of s_full[i]: c = 0 the prologue commit of QK(i), then the
+    // retirement of step(2(c-1)+i)).  A parity wait is only sound when the barrier is neither a full cycle ahead of nor
+    // behind the waiter (tests/test_alt_protocol_model.py):
+    //   * S(j) by the owner of tile j: it follows s_full[j&1] completion by completion;
+    //   * step(j-1) by the owner of tile j (correction): at that point step(j-3) has retired (S(j) was ready) and step(j+1)
+    //     cannot have (the in-order MMA warp still waits for this warpgroup's p_full(j)), so the barrier is at most one
+    //     completion away;
+    //   * step(n_kv-1) in the epilogue: ONLY by the owner of the last tile; the other warpgroup — which may not have touched
+    //     that barrier for a while, or at all when n_kv == 1 — learns it through the named barrier both meet at.
+    auto wait_S_ready = [&](int t) { mbar_wait_wd(s_full + (t & 1), uint32_t(t >> 1) & 1u); };
+    auto wait_step_retired = [&](int t) { mbar_wait_wd(s_full + (t & 1), uint32_t((t >> 1) + 1) & 1u); };
+
     float m_own = kMaskValue;   // m(j) of this warpgroup's latest tile: the reference its partial sum d is relative to
     float d = 0.f;              // sum of P over THIS warpgroup's tiles, relative to m_own
 
@@ -205,7 +216,7 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (p.causal) limit = min(limit, p.causal_q_offset + q_row - j * BN + 1);
       const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && (j + 1) * BN > p.causal_q_offset + qt * BM + 1);
 
-      mbar_wait_wd(s_full + (j & 1), s_parity(j));
+      wait_S_ready(j);
       tc_fence_after();
 
       auto tile = [&](auto masked_tag) {
@@ -314,7 +325,7 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         //      step(j-1) needs p_full(j-1) from the other warpgroup, whose own correction waits for step(j-2), which needs
         //      p_full(j-2) — signalled by this warpgroup one iteration ago.
         if (j > 0 && __any_sync(0xffffffffu, alpha_o != 1.0f)) {
-          mbar_wait_wd(s_full + ((j + 1) & 1), s_parity(j + 1));
+          wait_step_retired(j - 1);
           tc_fence_after();
           const uint64_t alpha2 = pack_f2(alpha_o, alpha_o);
 #pragma unroll
@@ -344,7 +355,13 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ---- epilogue: combine the two partial sums relative to the final max m(n_kv-1), then each warpgroup writes OC columns
     s_x[(wg * 2 + 0) * BM + row] = d;
     s_x[(wg * 2 + 1) * BM + row] = m_own;
+    if (n_kv > 0 && wg == ((n_kv - 1) & 1)) {   // owner of the last tile: O is final once step(n_kv-1) retired
+      wait_step_retired(n_kv - 1);
+      tc_fence_after();
+    }
+    tc_fence_before();
     alt_bar_sync();
+    tc_fence_after();
     const float d_o = s_x[((wg ^ 1) * 2 + 0) * BM + row], m_o = s_x[((wg ^ 1) * 2 + 1) * BM + row];
     const float m_fin = fmaxf(m_own, m_o);     // the running max is non-decreasing, so the later tile's value is the larger
     d = d * ex2_approx(m_own - m_fin) + d_o * ex2_approx(m_o - m_fin);
@@ -356,9 +373,7 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float* vs = p.v_scale ? p.v_scale + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D + wg * OC : nullptr;
     const float* vm = p.v_mean ? p.v_mean + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D + wg * OC : nullptr;
     if (n_kv > 0) {
-      mbar_wait_wd(s_full + ((n_kv + 1) & 1), s_parity(n_kv + 1));
-      tc_fence_after();
-      const float inv = rcp_approx(d);
+      const float inv = rcp_approx(d);   // O is final: the owner of the last tile saw step(n_kv-1) retire before the barrier above
 #pragma unroll
       for (int ch = 0; ch < OC / 32; ++ch) {
         uint32_t r[32];
