@@ -152,3 +152,36 @@ def test_lazy_rescale_numerics():
     exact, lazy = moved_fraction(None), moved_fraction(3)
     print(f"warp-tiles that rescale O: exact rule {exact:.2f}, tau=3 {lazy:.3f}")
     assert exact > 0.5 and lazy < 0.15
+
+
+def test_alternating_tile_row_sums_combine_to_the_sequential_sum():
+    """csrc/attn_alt.cu: warpgroup w accumulates d_w = sum over ITS tiles of sum_i P(j)_i relative to the max of its latest
+    tile; the epilogue combines d = d_0 2^(m_0 - m_fin) + d_1 2^(m_1 - m_fin).  Against the sequential update_mdo recurrence
+    d = d * 2^(m_old - m_new) + sum(P) (attn_utils.cuh:377-458) the result differs by fp32 rounding only — also with the lazy
+    max (tau = 3), where m(j) is the maximum IN USE, not the true one."""
+    g = np.random.default_rng(3)
+    for tau in (0, 3):
+        for n_kv in (1, 2, 3, 8, 33):
+            S = (g.standard_normal((64, n_kv, 64)) * 1.5 + g.standard_normal((64, n_kv, 1))).astype(np.float32)   # log2-domain logits
+            m = np.full(64, -5e6, np.float32)
+            d_seq = np.zeros(64, np.float32)
+            d_w = [np.zeros(64, np.float32), np.zeros(64, np.float32)]
+            m_w = [np.full(64, -5e6, np.float32), np.full(64, -5e6, np.float32)]
+            for j in range(n_kv):
+                mx = S[:, j].max(-1)
+                if tau:
+                    m_true = np.maximum(m, mx - np.float32(8.807 - tau))
+                    m_new = np.where(m_true - m > tau, m_true, m).astype(np.float32)
+                else:
+                    m_new = np.maximum(m, mx - np.float32(8.807))
+                P = np.exp2(S[:, j] - m_new[:, None]).astype(np.float32)
+                assert P.max() <= 448.0 * (1 + 1e-6)
+                d_seq = (d_seq * np.exp2(m - m_new) + P.sum(-1)).astype(np.float32)
+                w = j & 1
+                d_w[w] = (d_w[w] * np.exp2(m_w[w] - m_new) + P.sum(-1)).astype(np.float32)
+                m_w[w] = m_new
+                m = m_new
+            m_fin = np.maximum(m_w[0], m_w[1])
+            assert np.array_equal(m_fin, m)
+            d_alt = d_w[0] * np.exp2(m_w[0] - m_fin) + d_w[1] * np.exp2(m_w[1] - m_fin)
+            assert np.allclose(d_alt, d_seq, rtol=2e-6, atol=0), (tau, n_kv)
