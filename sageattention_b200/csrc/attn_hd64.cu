@@ -212,7 +212,14 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if constexpr (MASKED) c = (v == kIntSentinel) ? kMaskValue : c;
           mx = fmaxf(mx, c);
         }
+#ifdef SAB_LAZY_RESCALE
+        // opt-in build (see attn.cu): the max moves only when it grew by more than 2^tau, so the in-line O rescale below — about
+        // 70 of this issue-bound kernel's ~420 warp instructions per tile when it runs — happens in a few percent of the tiles
+        const float m_true = fmaxf(m, mx - (kFp8Offset - float(SAB_LAZY_RESCALE)));
+        const float m_new = (m_true - m > float(SAB_LAZY_RESCALE)) ? m_true : m;
+#else
         const float m_new = fmaxf(m, mx - kFp8Offset);   // update_mdo, attn_utils.cuh:377-396
+#endif
         const float alpha = ex2_approx(m - m_new);
         d *= alpha;
         m = m_new;
