@@ -103,14 +103,30 @@ def flops(B, H, Sq, Sk, D, causal=False):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
+METRIC = "attention TFLOPS (qk_int8_pv_fp8, hd=128, non-causal; 4*B*H*S^2*D / t)"
+WORKLOAD_N1 = "configs[1]: qk_int8_pv_fp8 hd=128 seq=8192 causal=False B=4 H=32 (reference bench defaults), bf16"
+
+
+def workload_sp(world):
+    return (f"configs[4]: sequence-parallel sageattn hd=128 seq=32768 B=1 H=32 non-causal, Q rows sharded over {world} ranks, "
+            "INT8 K / FP8 V all-gathered over NCCL")
+
+
 def run_reference(args):
-    """Reference algorithm on host cores: CPU port (oracle/sage_oracle.py), bounded sample of configs[1]."""
+    """Reference algorithm on host cores: CPU port (oracle/sage_oracle.py) on a bounded sample of the SAME workload the
+    other arm runs at this N (configs[1] at N=1: a B=1,H=8 slice; configs[4] at N>1: a B=1,H=1 slice of S=32768); rank 0 only."""
     import torch
     from oracle import sage_oracle as O
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B, H, S, D = 1, 8, 8192, 128
+    D = 128
+    if args.gpus == 1:
+        B, H, S, full = 1, 8, 8192, (4, 32, 8192)
+        workload = WORKLOAD_N1
+    else:
+        B, H, S, full = 1, 1, 32768, (1, 32, 32768)
+        workload = workload_sp(args.gpus)
     torch.manual_seed(0)
     q, k, v = (torch.randn(B, H, S, D).to(torch.bfloat16) for _ in range(3))
     cores = torch.get_num_threads()
@@ -123,14 +139,15 @@ def run_reference(args):
         f()
     dt = (time.perf_counter() - t0) / steps
     val = flops(B, H, S, S, D) / dt / 1e12
-    sample = f"B={B} H={H} slice of configs[1] (S={S}, D={D}, bf16), {steps} steps"
+    sample = f"B={B} H={H} slice (S={S}, D={D}, bf16) of the workload, {steps} steps; TFLOP/s is size-independent per head"
     print(json.dumps({
-        "impl": "reference", "metric": "attention TFLOPS (qk_int8_pv_fp8, hd=128, seq=8192, non-causal)", "value": val,
+        "impl": "reference", "metric": METRIC, "value": val,
         "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "int8+fp8(e4m3), fp32 softmax",
-        "data": "synthetic randn",
-        "config": {"workload": "configs[1] qk_int8_pv_fp8 hd=128 seq=8192 causal=False (bounded CPU sample: B=1,H=8)",
-                   "B": B, "H": H, "S": S, "D": D},
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "int8 (QK^T) + fp8-e4m3 (PV), fp32 softmax/accumulate, bf16 I/O", "data": "synthetic randn",
+        "config": {"workload": workload, "B": full[0], "H": full[1], "S": full[2], "D": D, "qk_quant_gran": "per_thread",
+                   "pv_accum_dtype": "fp32+fp16", "smooth_k": True,
+                   "sample": f"bounded CPU sample: B={B}, H={H} of B={full[0]}, H={full[1]}"},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -168,7 +185,7 @@ def run_ours(args):
 
     if world == 1:
         B, H, S = 4, 32, 8192
-        workload = "configs[1]: qk_int8_pv_fp8 hd=128 seq=8192 causal=False B=4 H=32 (reference bench defaults), bf16"
+        workload = WORKLOAD_N1
         q, k, v = (torch.randn(B, H, S, D, device=dev, dtype=dtype) for _ in range(3))
         step = lambda: sab.sageattn(q, k, v, tensor_layout="HND", is_causal=False)
         total_flops = flops(B, H, S, S, D)
@@ -179,8 +196,7 @@ def run_ours(args):
         B, H, S = 1, 32, 32768
         assert S % (world * 128) == 0
         Sl = S // world
-        workload = (f"configs[4]: sequence-parallel sageattn hd=128 seq=32768 B=1 H=32 non-causal, Q rows sharded over {world} ranks, "
-                    "INT8 K / FP8 V all-gathered over NCCL")
+        workload = workload_sp(world)
         # per-rank shards shrink with N (32 MB per tensor at N=8): rotate over enough independent input sets that the
         # bytes touched between two uses of the same set exceed twice the 126 MB L2 (timing rule: inputs larger than L2)
         per_set = 3 * B * H * Sl * D * 2
@@ -336,7 +352,7 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": "attention TFLOPS (qk_int8_pv_fp8, hd=128, non-causal; 4*B*H*S^2*D / t)", "value": value, "unit": "TFLOP/s",
+            "metric": METRIC, "value": value, "unit": "TFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "int8 (QK^T) + fp8-e4m3 (PV), fp32 softmax/accumulate, bf16 I/O",
             "data": "synthetic randn, random-init (no datasets/checkpoints offline)",
