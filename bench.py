@@ -193,6 +193,9 @@ def run_ours(args):
         scaling = "weak"
     else:
         from sageattention_b200 import parallel
+        # SAB_SP_FUSED_GATHER=1: peer copies + per-segment flags inside ONE attention launch instead of the NCCL all-gather
+        # before it (sageattention_b200/parallel.py; opt-in until it has been validated on GPUs)
+        fused_gather = os.environ.get("SAB_SP_FUSED_GATHER", "0") == "1"
         B, H, S = 1, 32, 32768
         assert S % (world * 128) == 0
         Sl = S // world
@@ -208,7 +211,7 @@ def run_ours(args):
         def step():
             a, b, c = sets[turn[0] % n_sets]
             turn[0] += 1
-            return parallel.sageattn_sp(a, b, c, tensor_layout="HND", is_causal=False)
+            return parallel.sageattn_sp(a, b, c, tensor_layout="HND", is_causal=False, fused_gather=fused_gather)
         total_flops = flops(B, H, S, S, D)
         launches_per_step = 9
         scaling = "strong"
@@ -325,7 +328,7 @@ def run_ours(args):
 
         def e2e_step():
             qd.copy_(qh, non_blocking=True); kd.copy_(kh, non_blocking=True); vd.copy_(vh, non_blocking=True)
-            oo = parallel.sageattn_sp(qd, kd, vd, tensor_layout="HND", is_causal=False)
+            oo = parallel.sageattn_sp(qd, kd, vd, tensor_layout="HND", is_causal=False, fused_gather=fused_gather)
             oh.copy_(oo, non_blocking=True)
         for _ in range(2):
             e2e_step()
@@ -361,7 +364,9 @@ def run_ours(args):
                        "l2": ("inputs (3 x %d MB per rank) exceed the 126 MB L2; no flush" % (B * H * S * D * 2 // 2 ** 20)) if world == 1 else
                              ("rotating over %d independent input sets of 3 x %d MB per rank (> 2 x the 126 MB L2 between reuses); no flush"
                               % (n_sets, B * H * (S // world) * D * 2 // 2 ** 20)),
-                       "step": "full sageattn(): K-mean + INT8 quant Q/K + FP8 quant V + fused attention"},
+                       "step": "full sageattn(): K-mean + INT8 quant Q/K + FP8 quant V + fused attention",
+                       **({"kv_exchange": "peer copies + segment flags inside the attention launch" if fused_gather else
+                           "NCCL all_gather of INT8 K / FP8 V before the attention launch"} if world > 1 else {})},
             "roofline": roof, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "cpu_baseline": cpu_baseline,
             "context": {"h100_published_kernel_tops_hd128_8k_noncausal": 900, "cached_kv": cached_kv,

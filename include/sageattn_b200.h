@@ -221,6 +221,22 @@ int sab_qk_int8_sv_f16_attn_masked(const int8_t* q_int8, const int8_t* k_int8, c
                                    int64_t mask_stride_b, int64_t mask_stride_h, int64_t mask_stride_m,
                                    int64_t mask_stride_n, void* stream);
 
+/* Sequence-parallel attention with the K/V gather fused into the launch (no reference counterpart: the reference ships no
+ * sequence-parallel operator, example/parallel_sageattn_cogvideo.py:44-51 only wires sageattn into xfuser).  Same tensors as the
+ * kv_seg_len > 0 form of sab_qk_int8_sv_f8_attn (k_int8 [P*B,Hkv,kv_seg_len,D], v_fp8 [P*B,Hkv,D,kv_seg_len], rank-major), but
+ * the segments may still be arriving: the kernel's TMA producer waits until
+ *     seg_flags[(kv_head / heads_per_flag) * (Skv / kv_seg_len) + segment] == seg_epoch      (32-bit, system-scope acquire)
+ * before it loads the first tile of a segment.  The caller writes each flag in stream order behind the copies that fill that
+ * (KV-head group, segment) — e.g. cudaMemcpyAsync from peer memory followed by cuStreamWriteValue32 on a second stream — and
+ * passes a fresh epoch per call, so flags never need resetting.  The copies and flag writes must not need SMs that the
+ * waiting CTAs occupy (copy engines + stream memory operations do not).  Dense, non-causal. */
+int sab_qk_int8_sv_f8_attn_sp(const int8_t* q_int8, const int8_t* k_int8, const uint8_t* v_fp8, void* out, float* lse,
+                              const float* q_scale, const float* k_scale, const float* v_scale, int out_dtype, int B, int Hq,
+                              int Hkv, int Sq, int Skv, int D, int64_t q_stride_b, int64_t q_stride_h, int64_t q_stride_s,
+                              int64_t k_stride_b, int64_t k_stride_h, int64_t k_stride_s, int64_t v_s_pad, int64_t o_stride_b,
+                              int64_t o_stride_h, int64_t o_stride_s, int q_gran, int k_gran, float sm_scale, int kv_seg_len,
+                              const uint32_t* seg_flags, uint32_t seg_epoch, int heads_per_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,8 @@ EXPORTS = {
                                        [c_void_p, c_int] + [c_int64] * 4 + [c_void_p]),
     "sab_qk_int8_sv_f8_attn": (c_int, [c_void_p] * 9 + [c_int] * 7 + [c_int64] * 10 + [c_int, c_int, c_int, c_float, c_int] +
                                [c_void_p] * 5 + [c_int, c_int, c_int, c_void_p, c_void_p]),
+    "sab_qk_int8_sv_f8_attn_sp": (c_int, [c_void_p] * 8 + [c_int] * 7 + [c_int64] * 10 + [c_int, c_int, c_float, c_int] +
+                                  [c_void_p, ctypes.c_uint32, c_int, c_void_p]),
 }
 
 _lib = None

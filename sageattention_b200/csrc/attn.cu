@@ -28,7 +28,9 @@ constexpr int kNumThreads = 384;  // warpgroups: 0-3 softmax, 4-7 correction, 8 
 // reference's sageattn_qk_int8_pv_fp16_triton / sageattn_varlen kernels (triton/attn_qk_int8_per_block.py:22-128).
 // kMask (kPV16 only): attn_mask of sageattn_qk_int8_pv_fp16_triton — a bool mask marks elements like the out-of-range
 // keys (integer sentinel), an additive bias takes the float path `tile_bias` below.
-template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false>
+// kSeg: sequence-parallel form whose K/V segments arrive WHILE the kernel runs (peer copies on another stream): the TMA
+// producer polls one flag per (KV-head group, segment) before the first tile of a segment (AttnParams::seg_flags).
+template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false, bool kSeg = false>
 __global__ void __launch_bounds__(kNumThreads, 2)
 sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -116,6 +118,7 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (lane == 0 && n_kv > 0) {
         mbar_expect_tx(q_full, Q_BYTES);
         tma_load_4d(sQ, &tmQ, q_full, 0, q_off + qt * BM, h, tb);
+        [[maybe_unused]] int ready_seg = -1;
         for (int j = 0; j < n_kv; ++j) {
           const int s = j % NS;
           const uint32_t ph = (j / NS) & 1;
@@ -124,6 +127,18 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int seg = (j * BN) / p.kv_seg_len;
             kc = vc = j * BN - seg * p.kv_seg_len;
             kb = seg * p.B + b;
+            if constexpr (kSeg) {
+              if (seg != ready_seg) {   // first tile of a segment: has the peer copy of this (head group, segment) landed?
+                const uint32_t* flag = p.seg_flags + (hk / p.seg_heads) * (p.Sk / p.kv_seg_len) + seg;
+                const long long t0 = clock64();
+                while (ld_acquire_sys_u32(flag) != p.seg_epoch) {
+                  __nanosleep(200);
+                  if (clock64() - t0 > (8ll << 30)) __trap();   // ~4 s: the copies never came; fail the launch instead of hanging the GPU
+                }
+                fence_proxy_async_all();
+                ready_seg = seg;
+              }
+            }
           }
           mbar_wait_wd(kv_empty + s, ph ^ 1);
           mbar_expect_tx(kv_full + s, K_TILE + V_TILE);
@@ -682,27 +697,27 @@ template <int D, bool kKT, typename OutT>
 int launch_attn_alt(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                     cudaStream_t stream);
 
-template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false>
+template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false, bool kSeg = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  if (!kPV16 && use_pair_kernel()) {
+  if (!kPV16 && !kSeg && use_pair_kernel()) {
     dim3 g2((grid.x + 1) / 2, grid.y, grid.z);
     return launch_attn_pair<D, kKT, OutT>(tq, tk, tv, p, g2, stream);
   }
-  if constexpr (!kPV16) {
+  if constexpr (!kPV16 && !kSeg) {
     if (attn_kernel_mode() == 2 && p.dbg == nullptr) return launch_attn_split<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
   }
-  if constexpr (D == 128 && !kPV16) {
+  if constexpr (D == 128 && !kPV16 && !kSeg) {
     if (attn_kernel_mode() == 3 && p.dbg == nullptr) return launch_attn_alt<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
   }
-  if constexpr (D == 64 && !kPV16) {
+  if constexpr (D == 64 && !kPV16 && !kSeg) {
     if (use_hd64_kernel() && p.dbg == nullptr) return launch_attn_hd64<kKT, OutT>(tq, tk, tv, p, grid, stream);
   }
   constexpr int NS = kPV16 ? ((D == 128) ? 3 : 6) : ((D == 128) ? 5 : 10);
   // Q tile + NS x (K + V^T 64-key tile) + alpha hand-off + barriers (97.5 KB at hd128): two CTAs per SM (TMEM: 2 x 256 columns)
   size_t smem = size_t(BM) * D + size_t(NS) * (BN * D + BN * D * (kPV16 ? 2 : 1)) + 2 * BM * sizeof(float) + 512;
   if (smem < 80 * 1024) smem = 80 * 1024;
-  auto kern = sage_attn_fwd_kernel<D, kKT, OutT, kPV16, kMask>;
+  auto kern = sage_attn_fwd_kernel<D, kKT, OutT, kPV16, kMask, kSeg>;
   static bool configured = false;
   if (!configured) {
     SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -720,6 +735,13 @@ struct MaskArgs {
   const void* ptr; int kind; int64_t sb, sh, sm, sn;
 };
 static thread_local const MaskArgs* tl_mask = nullptr;
+// segment flags of the fused sequence-parallel entry point, handed to attn_entry by sab_qk_int8_sv_f8_attn_sp (same thread)
+struct SegArgs {
+  const uint32_t* flags;
+  uint32_t epoch;
+  int heads_per_flag;
+};
+static thread_local const SegArgs* tl_seg = nullptr;
 
 static int attn_entry(int pv16, const int8_t* q_int8, const int8_t* k_int8, const uint8_t* v_fp8, void* out,
                                       float* lse, const float* q_scale, const float* k_scale, const float* v_scale,
@@ -814,6 +836,22 @@ static int attn_entry(int pv16, const int8_t* q_int8, const int8_t* k_int8, cons
     if (bf) return launch_attn<64, false, __nv_bfloat16, true, true>(tq, tk, tv, p, grid, s);
     return launch_attn<64, false, __half, true, true>(tq, tk, tv, p, grid, s);
   }
+  if (tl_seg != nullptr) {
+    SAB_REQUIRE(!pv16 && kv_seg_len > 0 && !is_causal && debug_dump == nullptr, SAB_ERR_UNSUPPORTED,
+                "segment flags need the sequence-parallel INT8/FP8 form (kv_seg_len > 0), non-causal");
+    SAB_REQUIRE(tl_seg->flags != nullptr && tl_seg->heads_per_flag > 0 && Hkv % tl_seg->heads_per_flag == 0, SAB_ERR_INVALID,
+                "segment flags: null pointer or heads_per_flag (%d) does not divide num_kv_heads (%d)", tl_seg->heads_per_flag, Hkv);
+    p.seg_flags = tl_seg->flags; p.seg_epoch = tl_seg->epoch; p.seg_heads = tl_seg->heads_per_flag;
+#define SAB_LAUNCH_SEG(DD, KT, T) return launch_attn<DD, KT, T, false, false, true>(tq, tk, tv, p, grid, s)
+    if (D == 128) {
+      if (kt) { if (bf) SAB_LAUNCH_SEG(128, true, __nv_bfloat16); else SAB_LAUNCH_SEG(128, true, __half); }
+      else    { if (bf) SAB_LAUNCH_SEG(128, false, __nv_bfloat16); else SAB_LAUNCH_SEG(128, false, __half); }
+    } else {
+      if (kt) { if (bf) SAB_LAUNCH_SEG(64, true, __nv_bfloat16); else SAB_LAUNCH_SEG(64, true, __half); }
+      else    { if (bf) SAB_LAUNCH_SEG(64, false, __nv_bfloat16); else SAB_LAUNCH_SEG(64, false, __half); }
+    }
+#undef SAB_LAUNCH_SEG
+  }
 #define SAB_LAUNCH(DD, KT, T)                                                      \
   do {                                                                             \
     if (pv16) return launch_attn<DD, KT, T, true>(tq, tk, tv, p, grid, s);         \
@@ -844,6 +882,23 @@ extern "C" int sab_qk_int8_sv_f8_attn(const int8_t* q_int8, const int8_t* k_int8
                     q_stride_b, q_stride_h, q_stride_s, k_stride_b, k_stride_h, k_stride_s, v_s_pad, o_stride_b, o_stride_h,
                     o_stride_s, is_causal, q_gran, k_gran, sm_scale, fold_sm_scale, cu_seqlens_q, cu_seqlens_k, cu_pad_v,
                     cu_q_scale, cu_k_scale, max_seqlen_q, causal_q_offset, kv_seg_len, debug_dump, stream);
+}
+
+extern "C" int sab_qk_int8_sv_f8_attn_sp(const int8_t* q_int8, const int8_t* k_int8, const uint8_t* v_fp8, void* out,
+                                         float* lse, const float* q_scale, const float* k_scale, const float* v_scale,
+                                         int out_dtype, int B, int Hq, int Hkv, int Sq, int Skv, int D, int64_t q_stride_b,
+                                         int64_t q_stride_h, int64_t q_stride_s, int64_t k_stride_b, int64_t k_stride_h,
+                                         int64_t k_stride_s, int64_t v_s_pad, int64_t o_stride_b, int64_t o_stride_h,
+                                         int64_t o_stride_s, int q_gran, int k_gran, float sm_scale, int kv_seg_len,
+                                         const uint32_t* seg_flags, uint32_t seg_epoch, int heads_per_flag, void* stream) {
+  const SegArgs a{seg_flags, seg_epoch, heads_per_flag};
+  tl_seg = &a;
+  const int st = attn_entry(0, q_int8, k_int8, v_fp8, out, lse, q_scale, k_scale, v_scale, nullptr, out_dtype, B, Hq, Hkv, Sq, Skv,
+                            D, q_stride_b, q_stride_h, q_stride_s, k_stride_b, k_stride_h, k_stride_s, v_s_pad, o_stride_b,
+                            o_stride_h, o_stride_s, 0, q_gran, k_gran, sm_scale, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                            0, kv_seg_len, nullptr, stream);
+  tl_seg = nullptr;
+  return st;
 }
 
 extern "C" int sab_qk_int8_sv_f16_attn(const int8_t* q_int8, const int8_t* k_int8, const void* v_f16t, void* out, float* lse,

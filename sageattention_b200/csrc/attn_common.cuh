@@ -55,6 +55,11 @@ struct AttnParams {
   const void* mask;      // nullable
   int mask_kind;         // 1: bool (uint8, false = masked out), 2: additive bias in the output dtype (fp16 / bf16)
   int64_t mask_sb, mask_sh, mask_sm, mask_sn;   // element strides
+  // sequence-parallel gather fused into the launch (kSeg instantiations): K/V segment `seg` of KV-head group g is complete in
+  // this GPU's memory once seg_flags[g * n_segments + seg] == seg_epoch (written in stream order behind the peer copies)
+  const uint32_t* seg_flags;   // nullable
+  uint32_t seg_epoch;
+  int seg_heads;               // KV heads per flag group
 };
 
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {

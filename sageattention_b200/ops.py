@@ -207,6 +207,33 @@ def _(query, key, value, output, query_scale, key_scale, value_scale, value_mean
     return torch.empty((0,), dtype=torch.float32, device=query.device)
 
 
+@torch.library.custom_op("sageattention_b200::qk_int8_sv_f8_attn_sp", mutates_args=("output",), device_types="cuda")
+def qk_int8_sv_f8_attn_sp(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, output: torch.Tensor,
+                          query_scale: torch.Tensor, key_scale: torch.Tensor, value_scale: torch.Tensor, q_quant_gran: int,
+                          k_quant_gran: int, sm_scale: float, kv_seg_len: int, seg_flags: torch.Tensor, seg_epoch: int,
+                          heads_per_flag: int) -> None:
+    """Sequence-parallel attention whose K/V segments may still be arriving (include/sageattn_b200.h, sab_qk_int8_sv_f8_attn_sp):
+    HND tensors, key [P*B,Hkv,kv_seg_len,D] / value [P*B,Hkv,D,kv_seg_len] rank-major, seg_flags int32 [Hkv/heads_per_flag * P];
+    the kernel waits for seg_flags[group * P + segment] == seg_epoch before the first tile of a segment.  Non-causal."""
+    B, Hq, Sq, D = query.shape
+    Hkv = key.size(1)
+    P = key.size(0) // B
+    assert seg_flags.dtype == torch.int32 and seg_flags.is_contiguous() and seg_flags.numel() >= (Hkv // heads_per_flag) * P
+    qs, ks, os_ = _bhs_strides(query, 1), _bhs_strides(key, 1), _bhs_strides(output, 1)
+    with torch.cuda.device(query.device):
+        check(lib().sab_qk_int8_sv_f8_attn_sp(query.data_ptr(), key.data_ptr(), value.data_ptr(), output.data_ptr(), None,
+                                              query_scale.data_ptr(), key_scale.data_ptr(), value_scale.data_ptr(), _dt(output),
+                                              B, Hq, Hkv, Sq, P * kv_seg_len, D, *qs, *ks, value.size(-1), *os_, q_quant_gran,
+                                              k_quant_gran, float(sm_scale), kv_seg_len, seg_flags.data_ptr(),
+                                              int(seg_epoch) & 0xFFFFFFFF, heads_per_flag, _stream(query)))
+
+
+@qk_int8_sv_f8_attn_sp.register_fake
+def _(query, key, value, output, query_scale, key_scale, value_scale, q_quant_gran, k_quant_gran, sm_scale, kv_seg_len,
+      seg_flags, seg_epoch, heads_per_flag):
+    return None
+
+
 @torch.library.custom_op("sageattention_b200::qk_int8_sv_f8_attn_varlen", mutates_args=("output",), device_types="cuda")
 def qk_int8_sv_f8_attn_varlen(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, output: torch.Tensor,
                               query_scale: torch.Tensor, key_scale: torch.Tensor, value_scale: torch.Tensor,

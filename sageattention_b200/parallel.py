@@ -65,11 +65,63 @@ def _comm_stream(dev):
     return _COMM_STREAMS[key]
 
 
+# ------------------------------------------------------------------ gather fused into the attention launch (opt-in)
+def pull_schedule(world: int, rank: int, n_chunks: int):
+    """Issue order of the peer copies: KV-head chunk by chunk (the attention grid runs the heads in order), within a chunk
+    the own shard first and then the peers in ring order starting after this rank, so that at any time every rank pulls
+    from a different peer.  Element = (chunk, source rank); the flag of that element is index chunk * world + source."""
+    return [(c, (rank + step) % world) for c in range(n_chunks) for step in range(world)]
+
+
+class _FusedGatherWorkspace:
+    """The gathered K / V buffers the attention kernel reads, allocated as SYMMETRIC (peer-mapped) memory: rank r quantises its
+    shard straight into segment r of its own buffers, where the peers read it; so the own segment needs no copy at all and every
+    transfer is a peer-to-peer copy (DMA engines).  Plus the arrival flags and the call epoch.  One per (group, shapes)."""
+
+    def __init__(self, group, dev, B, Hk, Sl, D, world, n_chunks, rank):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.nk = B * Hk * Sl * D                       # bytes of one INT8 K shard (== one FP8 V shard)
+        self.world, self.rank, self.B = world, rank, B
+        self.buf = symm_mem.empty(2 * world * self.nk, dtype=torch.uint8, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.shape_k, self.shape_v = (world * B, Hk, Sl, D), (world * B, Hk, D, Sl)
+        self.k_all = self.buf[:world * self.nk].view(torch.int8).view(self.shape_k)
+        self.v_all = self.buf[world * self.nk:].view(torch.float8_e4m3fn).view(self.shape_v)
+        self.k_local = self.k_all[rank * B:(rank + 1) * B]
+        self.v_local = self.v_all[rank * B:(rank + 1) * B]
+        self.flags = torch.zeros((n_chunks * world,), dtype=torch.int32, device=dev)
+        self.epoch = 0
+
+    def peer_shard(self, src):
+        """Views of rank `src`'s OWN segment inside rank `src`'s buffers (peer-mapped)."""
+        k = self.hdl.get_buffer(src, self.shape_k, torch.int8, 0)
+        v = self.hdl.get_buffer(src, self.shape_v, torch.uint8, self.world * self.nk).view(torch.float8_e4m3fn)
+        return k[src * self.B:(src + 1) * self.B], v[src * self.B:(src + 1) * self.B]
+
+
+_FUSED_WS = {}
+
+
+def _fused_workspace(group, dev, B, Hk, Sl, D, world, n_chunks, rank):
+    key = (id(group), dev.index, B, Hk, Sl, D, world, n_chunks)
+    if key not in _FUSED_WS:
+        _FUSED_WS[key] = _FusedGatherWorkspace(group, dev, B, Hk, Sl, D, world, n_chunks, rank)
+    return _FUSED_WS[key]
+
+
 # ------------------------------------------------------------------ the SP operator
 def sageattn_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout: str = "HND", is_causal: bool = False,
                 qk_quant_gran: str = "per_thread", sm_scale: Optional[float] = None, pv_accum_dtype: str = "fp32+fp16",
-                smooth_k: bool = True, group=None, overlap_chunks: int = 1, **kwargs: Any) -> torch.Tensor:
-    """Sequence-parallel `sageattn_qk_int8_pv_fp8_cuda`: local shards in, local output shard out."""
+                smooth_k: bool = True, group=None, overlap_chunks: int = 1, fused_gather: bool = False,
+                gather_chunks: int = 4, **kwargs: Any) -> torch.Tensor:
+    """Sequence-parallel `sageattn_qk_int8_pv_fp8_cuda`: local shards in, local output shard out.
+
+    fused_gather=True (non-causal; NOT YET RUN ON GPUs — written at the end of round 1 without GPU access): the K/V exchange
+    is not an NCCL collective before the attention launch but peer copies that run WHILE the one attention launch computes:
+    every rank quantises its shard into a symmetric (peer-mapped) buffer, a side stream pulls the peers' shards KV-head chunk
+    by chunk with the copy engines (no SMs) and raises one flag per (chunk, segment) in stream order, and the kernel's TMA
+    producer waits for the flag of a segment before its first tile (csrc/attn.cu kSeg).  Same data in the same order as the
+    collective path, hence the same bits out."""
     if group is None and not dist.is_initialized():
         raise RuntimeError("sageattn_sp needs an initialised torch.distributed process group (NCCL)")
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -106,8 +158,13 @@ def sageattn_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout
     v_amax = global_abs_max(vmax, vmin, group)
 
     # 3. quantise the local shards (HND int8 buffers so the all-gather output is [P*B,H,Sl,D])
+    fused = bool(fused_gather) and world > 1
+    if fused:
+        assert not is_causal, "fused_gather supports non-causal attention only"
+        n_fc = gather_chunks if (gather_chunks and Hk % gather_chunks == 0) else 1
+        ws = _fused_workspace(group, dev, B, Hk, Sl, D, world, n_fc, rank)
     q_int8 = torch.empty((B, Hq, Sl, D), dtype=torch.int8, device=dev)
-    k_int8 = torch.empty((B, Hk, Sl, D), dtype=torch.int8, device=dev)
+    k_int8 = ws.k_local if fused else torch.empty((B, Hk, Sl, D), dtype=torch.int8, device=dev)
     qv = q if lay == 1 else q.transpose(1, 2)
     kv_ = k if lay == 1 else k.transpose(1, 2)
     vv = v if lay == 1 else v.transpose(1, 2)
@@ -124,9 +181,38 @@ def sageattn_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout
         ops.quant_per_thread_int8(qv, None, q_int8, q_scale, 1, False)
         ops.quant_per_thread_int8(kv_, kmean, k_int8, k_scale, 1, True)
     scale_max = 2.25 if pv_accum_dtype == "fp32+fp16" else 448.0
-    v_fp8 = torch.empty((B, Hk, D, Sl), dtype=torch.float8_e4m3fn, device=dev)
+    v_fp8 = ws.v_local if fused else torch.empty((B, Hk, D, Sl), dtype=torch.float8_e4m3fn, device=dev)
     v_scale = torch.empty((B, Hk, D), dtype=torch.float32, device=dev)
     ops.v_quant_with_amax(vv, v_fp8, v_amax, v_scale, 1, scale_max)
+
+    if fused:
+        from torch._C._distributed_c10d import _SymmetricMemory
+        o = torch.empty((B, Hq, Sl, D), dtype=dtype, device=dev)
+        ks_all = gather_scales(k_scale, group)               # tiny (B*Hk*S/64*{1,4} floats): ordinary collective, before the launch
+        cur = torch.cuda.current_stream(dev)
+        comm = _comm_stream(dev)
+        ws.hdl.barrier(channel=0)                            # every rank's quantised shard is in segment `rank` of its buffers
+        ws.epoch += 1
+        hc = Hk // n_fc
+        for c in range(n_fc):                                # the own segment is in place: its flags go up before the launch
+            _SymmetricMemory.stream_write_value32(ws.flags, c * world + rank, ws.epoch)
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):
+            for c, src in pull_schedule(world, rank, n_fc):
+                if src == rank:
+                    continue
+                pk, pv = ws.peer_shard(src)
+                for b in range(B):                           # a head range of one batch entry is contiguous: one peer memcpy
+                    ws.k_all[src * B + b, c * hc:(c + 1) * hc].copy_(pk[b, c * hc:(c + 1) * hc], non_blocking=True)
+                    ws.v_all[src * B + b, c * hc:(c + 1) * hc].copy_(pv[b, c * hc:(c + 1) * hc], non_blocking=True)
+                _SymmetricMemory.stream_write_value32(ws.flags, c * world + src, ws.epoch)
+            ws.hdl.barrier(channel=1)                        # all ranks finished pulling: segment `rank` may be rewritten
+        # the ONE attention launch, on the compute stream, not ordered after the copies: the kernel itself waits per segment
+        ops.qk_int8_sv_f8_attn_sp(q_int8, ws.k_all, ws.v_all, o, q_scale, ks_all, v_scale, gran, gran, sm_scale, Sl,
+                                  ws.flags, ws.epoch, hc)
+        cur.wait_stream(comm)                                # the next call's quantisation overwrites the staging buffers
+        o = o[..., :head_dim_og]
+        return o if lay == 1 else o.transpose(1, 2)
 
     # 4+5. all-gather the quantised K / V (+ K scales) over NVLink and attend.  Heads are independent, so the work is
     #      pipelined over KV-head chunks: NCCL gathers chunk c+1 on a side stream while the attention kernel runs on

@@ -30,6 +30,15 @@ for (B, H, Hk, S, D, causal, gran) in [(1, 4, 4, 1024 * world, 128, False, "per_
     err_n = (o_sp_n.transpose(1, 2).float() - o_sp.float()).abs().max().item()
     print(f"rank {rank} cfg {(B, H, Hk, S, D, causal, gran)} max-abs SP vs single {err:.3e}  NHD vs HND {err_n:.3e}", flush=True)
     ok = ok and err <= 4e-3 and err_n == 0.0     # K mean summation order may differ in the last fp32 bit -> rare 1-ulp km differences
+    # gather fused into the attention launch (opt-in until it has run on GPUs: SAB_TEST_FUSED_GATHER=1): same data in the same
+    # order as the collective path -> identical bits; twice, so that the epoch / staging-buffer reuse across calls is exercised
+    if os.environ.get("SAB_TEST_FUSED_GATHER", "0") == "1" and not causal:
+        for it in range(2):
+            o_f = parallel.sageattn_sp(q[:, :, sl].contiguous(), k[:, :, sl].contiguous(), v[:, :, sl].contiguous(), is_causal=False,
+                                       qk_quant_gran=gran, fused_gather=True, gather_chunks=2)
+            same = torch.equal(o_f, o_sp)
+            print(f"rank {rank} fused gather (call {it}) == collective path: {same}", flush=True)
+            ok = ok and same
     # Ulysses (head-parallel, two all_to_all): per-head statistics only -> bit-identical to the single-GPU call
     if H % world == 0 and Hk % world == 0:
         o_u = parallel.sageattn_ulysses(q[:, :, sl].contiguous(), k[:, :, sl].contiguous(), v[:, :, sl].contiguous(), is_causal=causal,

@@ -137,3 +137,19 @@ def test_ring_attention_gloo_world2():
     mp.spawn(_ring_worker, args=(world, port, ret), nprocs=world, join=True)
     for r in range(world):
         assert all(ret[r]), f"rank {r}: {ret[r]}"
+
+
+def test_fused_gather_pull_schedule():
+    """Issue order of the peer copies of sageattn_sp(fused_gather=True): every (chunk, source) exactly once, chunk-major (the
+    attention grid runs the heads in order), own shard first, and at every step all ranks pull from DIFFERENT peers."""
+    sys.path.insert(0, ROOT)
+    from sageattention_b200 import parallel
+    for world in (2, 3, 4, 8):
+        for n_chunks in (1, 2, 4):
+            scheds = [parallel.pull_schedule(world, r, n_chunks) for r in range(world)]
+            for r, s in enumerate(scheds):
+                assert sorted(s) == sorted((c, x) for c in range(n_chunks) for x in range(world))
+                assert [c for c, _ in s] == sorted(c for c, _ in s)
+                assert all(s[c * world][1] == r for c in range(n_chunks))
+            for i in range(n_chunks * world):
+                assert len({scheds[r][i][1] for r in range(world)}) == world
