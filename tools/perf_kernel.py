@@ -30,4 +30,25 @@ for (B, H, S, D, causal, gran) in shapes:
     ms = e0.elapsed_time(e1) / n
     fl = 4.0 * B * H * S * S * D / (2 if causal else 1)
     out.append(f"D{D} S{S} c{causal} {gran}: {fl / ms / 1e9:.0f}")
+if not (len(sys.argv) > 1 and sys.argv[1] == "short"):
+    # BASELINE configs[3]: sageattn_varlen, GQA Hq=32 / Hkv=8, hd=128, sequence lengths 512..16384 (whole call: quantisation + FP16-PV kernel)
+    lens = [512, 1024, 2048, 4096, 8192, 16384]
+    g = torch.Generator().manual_seed(0)
+    lens = [lens[i] for i in torch.randperm(len(lens), generator=g).tolist()]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    T = int(cu[-1])
+    q = torch.randn(T, 32, 128, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(T, 8, 128, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(T, 8, 128, device=dev, dtype=torch.bfloat16)
+    for causal in (False, True):
+        f = lambda: sab.sageattn_varlen(q, k, v, cu, cu, max(lens), max(lens), is_causal=causal)
+        for _ in range(3): f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): f()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        fl = sum(4.0 * 32 * L * L * 128 for L in lens) / (2 if causal else 1)
+        out.append(f"varlen GQA c{int(causal)} (whole call): {fl / ms / 1e9:.0f}")
 print(os.environ.get("SAB_LIB_PATH", "default"), " | ".join(out), flush=True)
