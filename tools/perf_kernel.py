@@ -35,7 +35,7 @@ if not (len(sys.argv) > 1 and sys.argv[1] == "short"):
     lens = [512, 1024, 2048, 4096, 8192, 16384]
     g = torch.Generator().manual_seed(0)
     lens = [lens[i] for i in torch.randperm(len(lens), generator=g).tolist()]
-    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+    cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32, device=dev)
     T = int(cu[-1])
     q = torch.randn(T, 32, 128, device=dev, dtype=torch.bfloat16)
     k = torch.randn(T, 8, 128, device=dev, dtype=torch.bfloat16)
