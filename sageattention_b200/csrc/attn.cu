@@ -718,11 +718,8 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   size_t smem = size_t(BM) * D + size_t(NS) * (BN * D + BN * D * (kPV16 ? 2 : 1)) + 2 * BM * sizeof(float) + 512;
   if (smem < 80 * 1024) smem = 80 * 1024;
   auto kern = sage_attn_fwd_kernel<D, kKT, OutT, kPV16, kMask, kSeg>;
-  static bool configured = false;
-  if (!configured) {
-    SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  if (int st = ensure_dynamic_smem(kern, smem, configured)) return st;
   kern<<<grid, kNumThreads, smem, stream>>>(tq, tk, tv, p);
   SAB_CUDA_OK(cudaGetLastError());
   return SAB_OK;

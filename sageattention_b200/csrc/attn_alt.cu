@@ -422,11 +422,8 @@ int launch_attn_alt(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
   size_t smem = size_t(BM) * D + size_t(NS) * 2 * BN * D + 6 * BM * sizeof(float) + 512;
   if (smem < 80 * 1024) smem = 80 * 1024;   // keep it at two CTAs per SM (TMEM: 2 x 256 columns)
   auto kern = sage_attn_alt_kernel<D, kKT, OutT>;
-  static bool configured = false;
-  if (!configured) {
-    SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  if (int st = ensure_dynamic_smem(kern, smem, configured)) return st;
   kern<<<grid, kAltThreads, smem, stream>>>(tq, tk, tv, p);
   SAB_CUDA_OK(cudaGetLastError());
   return SAB_OK;

@@ -79,6 +79,20 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// Host: opt a kernel into its dynamic shared-memory size once PER DEVICE (cudaFuncSetAttribute applies to the current
+// device only; a process that drives several GPUs — sageattn_host(device=...), tests — must set it on each).
+template <typename Kern>
+inline int ensure_dynamic_smem(Kern kern, size_t smem, bool (&done)[64]) {
+  int dev = 0;
+  SAB_CUDA_OK(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < 64;
+  if (!tracked || !done[dev]) {
+    SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    if (tracked) done[dev] = true;
+  }
+  return SAB_OK;
+}
+
 template <typename T>
 __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <>

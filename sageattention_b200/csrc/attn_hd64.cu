@@ -342,11 +342,8 @@ int launch_attn_hd64(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   constexpr int NS = 5;
   const size_t smem = size_t(BM) * 64 + size_t(NS) * 2 * BN * 64 + 256;   // 49.3 KB -> four CTAs per SM
   auto kern = sage_attn_hd64_kernel<kKT, OutT>;
-  static bool configured = false;
-  if (!configured) {
-    SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  if (int st = ensure_dynamic_smem(kern, smem, configured)) return st;
   kern<<<grid, kHd64Threads, smem, stream>>>(tq, tk, tv, p);
   SAB_CUDA_OK(cudaGetLastError());
   return SAB_OK;

@@ -457,11 +457,8 @@ int launch_attn_pair(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   constexpr int NS = (D == 128) ? 5 : 10;
   const size_t smem = size_t(2) * BM * D + size_t(NS) * 2 * LK * D + 2 * 2 * BM * sizeof(float) + 512;
   auto kern = sage_attn_pair_kernel<D, kKT, OutT>;
-  static bool configured = false;
-  if (!configured) {
-    SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  if (int st = ensure_dynamic_smem(kern, smem, configured)) return st;
   kern<<<grid, kPairThreads, smem, stream>>>(tq, tk, tv, p);
   SAB_CUDA_OK(cudaGetLastError());
   return SAB_OK;

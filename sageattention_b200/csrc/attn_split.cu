@@ -377,11 +377,8 @@ int launch_attn_split(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   size_t smem = size_t(BM) * D + size_t(NS) * 2 * BN * D + 4 * BM * sizeof(float) + 512;
   if (smem < 80 * 1024) smem = 80 * 1024;   // keep it at two CTAs per SM (TMEM: 2 x 256 columns)
   auto kern = sage_attn_split_kernel<D, kKT, OutT>;
-  static bool configured = false;
-  if (!configured) {
-    SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  if (int st = ensure_dynamic_smem(kern, smem, configured)) return st;
   kern<<<grid, kSplitThreads, smem, stream>>>(tq, tk, tv, p);
   SAB_CUDA_OK(cudaGetLastError());
   return SAB_OK;
