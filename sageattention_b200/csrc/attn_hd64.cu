@@ -241,8 +241,17 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const uint64_t f2 = pack_f2(__int2float_rn(int(s[i])), __int2float_rn(int(s[i + 1])));
             float y0, y1;
             unpack_f2(ffma2(f2, coef2[g], nm2), y0, y1);
+#ifdef SAB_POLY_EXP_PAIRS
+            if (((i >> 1) & 3) < SAB_POLY_EXP_PAIRS) {   // opt-in build: this pair on the FMA pipe (ptx.cuh ex2_poly2)
+              ex2_poly2(y0, y1, e[u], e[u + 1]);
+            } else {
+              e[u] = ex2_approx(y0);
+              e[u + 1] = ex2_approx(y1);
+            }
+#else
             e[u] = ex2_approx(y0);
             e[u + 1] = ex2_approx(y1);
+#endif
             if constexpr (MASKED) {
               e[u] = (i < limit) ? e[u] : 0.f;
               e[u + 1] = (i + 1 < limit) ? e[u + 1] : 0.f;

@@ -24,6 +24,7 @@ VARIANTS = {
     "all_chain": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_LATE_ALPHA"], "the three chain shorteners together (P stays bit-identical)"),
     "lazy3": (["SAB_LAZY_RESCALE=3"], "running max moves only when it grew by > 2^3: O rescale in ~3 % of the warp-tiles instead of ~80 %"),
     "all_chain_lazy3": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_LATE_ALPHA", "SAB_LAZY_RESCALE=3"], "chain shorteners + lazy rescale"),
+    "lazy3_poly1": (["SAB_LAZY_RESCALE=3", "SAB_POLY_EXP_PAIRS=1"], "lazy rescale + 25 % polynomial exp2 (the hd64 kernel is issue-bound: fewer rescale instructions make room for the polynomial)"),
     "defer_premax8": (["SAB_DEFER_PST", "SAB_PREMAX=8"], "both chain shorteners"),
     "defer_premax8_poly1": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_POLY_EXP_PAIRS=1"], "chain shorteners + 25 % polynomial exp2"),
 }
