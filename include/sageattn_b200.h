@@ -15,7 +15,7 @@
  *
  * Tensor convention: a "bhsd" tensor is addressed as ptr[b*stride_b + h*stride_h + s*stride_s + d]
  * (strides in ELEMENTS, innermost dimension contiguous) which covers both reference layouts
- * ("HND" [B,H,S,D] and "NHD" [B,S,H,D], tensor_layout 1 / 0 in csrc/qattn/*.cu).
+ * ("HND" [B,H,S,D] and "NHD" [B,S,H,D], tensor_layout 1 / 0 in the csrc/qattn launchers).
  */
 #ifndef SAGEATTN_B200_H_
 #define SAGEATTN_B200_H_
