@@ -91,3 +91,21 @@ def test_extensions_beyond_the_reference_surface_are_exported_and_guarded():
     from sageattention_b200.host import _chunks
     assert _chunks(2, 8, 2, 4) == [(0, 0, 4), (0, 4, 8), (1, 0, 4), (1, 4, 8)]
     assert _chunks(1, 6, 1, 4) == [(0, 0, 4), (0, 4, 6)]
+
+
+def test_plain_c_program_links_and_validates(tmp_path):
+    """tests/c/abi_smoke.c: a C (not C++) translation unit includes include/sageattn_b200.h, links libsageattn_b200.so with gcc
+    alone and gets status codes + messages back — the boundary really is a C ABI with plain pointers and sizes."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from sageattention_b200 import _capi
+    _capi.lib()
+    libdir = os.path.dirname(_capi._LIB_PATH)
+    exe = str(tmp_path / "abi_smoke")
+    r = subprocess.run(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+                        "-o", exe, "-L", libdir, "-lsageattn_b200", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "C_ABI_OK" in r.stdout, r.stdout + r.stderr
