@@ -38,12 +38,38 @@ def mk(shape, dtype, seed, outlier=False):
     return q, k, v.to(dtype)
 
 
+def xattn_fixture(qpb, att):
+    """2c. qo_len != kv_len (non-causal cross-attention) with head_dim 96 in bf16: the host glue of
+    sageattn_qk_int8_pv_fp16_triton zero-pads the head dim to 128 (core.py:262-271), keeps sm_scale = 96**-0.5 (:288-289), casts V to
+    fp16 (:297-298), and slices the output back (:327)."""
+    g = torch.Generator().manual_seed(777)
+    dtype, D, Dp = torch.bfloat16, 96, 128
+    q = torch.randn((1, 2, 192, D), generator=g).to(dtype)
+    k = (torch.randn((1, 2, 320, D), generator=g) + 3.0 * torch.randn((1, 2, 1, D), generator=g)).to(dtype)
+    v = (torch.randn((1, 2, 320, D), generator=g) + 1.0).to(dtype)
+    qp, kp, vp = (torch.nn.functional.pad(t, (0, Dp - D)) for t in (q, k, v))
+    km = kp.mean(dim=2, keepdim=True)
+    lse_corr = torch.matmul(qp, km.transpose(2, 3)).squeeze(-1).to(torch.float32)
+    sm_scale = 1.0 / (D ** 0.5)
+    q8, qs, k8, ks = qpb.per_block_int8(qp, kp, km=km, sm_scale=sm_scale)
+    o, lse = att.forward(q8, k8, vp.to(torch.float16), qs, ks, tensor_layout="HND", output_dtype=dtype, return_lse=True)
+    o = o[..., :D]
+    lse = lse / 1.44269504 + lse_corr * sm_scale
+    np.savez_compressed(f"{HERE}/attn_xattn_d96_bf16.npz", q=bits(q), k=bits(k), v=bits(v), o=bits(o), lse=lse.numpy(),
+                        causal=False, dtype=str(dtype))
+    print("wrote attn_xattn_d96_bf16")
+
+
 def main():
     qpb, qpt, qpbv = load("quant_per_block"), load("quant_per_thread"), load("quant_per_block_varlen")
     att, attc = load("attn_qk_int8_per_block"), load("attn_qk_int8_per_block_causal")
     attv, attvc = load("attn_qk_int8_block_varlen"), load("attn_qk_int8_per_block_causal_varlen")
 
     only_mask = "--only-mask" in sys.argv      # regenerate just the attn_mask fixtures (section 2b)
+    only_xattn = "--only-xattn" in sys.argv    # regenerate just the cross-attention / padded head-dim fixture (section 2c)
+    if only_xattn:
+        xattn_fixture(qpb, att)
+        return
 
     # ---- 1. quantisation fixtures (bit-exact targets) ----------------------------------------
     for name, shape, dtype, outlier in [] if only_mask else [
@@ -83,6 +109,9 @@ def main():
         np.savez_compressed(f"{HERE}/{name}.npz", q=bits(q), k=bits(k), v=bits(v), o=bits(o),
                             lse=lse.numpy(), causal=causal, dtype=str(dtype))
         print("wrote", name)
+
+    if not only_mask:
+        xattn_fixture(qpb, att)
 
     # ---- 2b. attn_mask of the Triton path (core.py:248-250, 310-325; attn_qk_int8_per_block.py:33-52) ----
     for name, shape, kind in [("attn_mask_bool_d64", (1, 2, 256, 64), "bool"), ("attn_mask_bias_d128", (1, 2, 200, 128), "bias")]:

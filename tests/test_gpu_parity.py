@@ -256,6 +256,20 @@ def test_triton_path_shell_vs_reference_triton_fixtures(env, name):
     assert (o.float() - o_ref.float()).abs().max().item() <= 4e-3
 
 
+@pytest.mark.skipif(os.environ.get("SAB_TEST_NEW_FIXTURES", "0") != "1",
+                    reason="fixture added at the end of round 1 without GPU access (set SAB_TEST_NEW_FIXTURES=1); unguard once green")
+def test_triton_path_shell_cross_attention_padded_head_dim(env):
+    """qo_len != kv_len, head_dim 96 (padded to 128, sm_scale from 96), bf16 (V cast to fp16): against the reference Triton
+    kernel's output (tests/golden/attn_xattn_d96_bf16.npz); one bf16 output ulp + the fp16-accumulate slack."""
+    sab, ops, O = env
+    z = np.load(f"{G}/attn_xattn_d96_bf16.npz")
+    q, k, v, o_ref = (_t(z[n], torch.bfloat16).cuda() for n in ("q", "k", "v", "o"))
+    o, lse = sab.sageattn_qk_int8_pv_fp16_triton(q, k, v, is_causal=False, return_lse=True)
+    assert o.shape == o_ref.shape
+    assert np.allclose(lse.cpu().numpy(), z["lse"], atol=2e-3)
+    assert (o.float() - o_ref.float()).abs().max().item() <= 2.0 ** -7 + 4e-3
+
+
 @pytest.mark.parametrize("name", ["attn_mask_bool_d64", "attn_mask_bias_d128"])
 def test_triton_path_attn_mask_vs_reference_triton_fixtures(env, name):
     """attn_mask of sageattn_qk_int8_pv_fp16_triton (core.py:248-250, 310-325; attn_qk_int8_per_block.py:33-52): bool mask

@@ -36,14 +36,16 @@ def test_quant_bit_exact(name):
     assert np.array_equal(qs.numpy(), z["ptn_qs"]) and np.array_equal(ks.numpy(), z["ptn_ks"])
 
 
-@pytest.mark.parametrize("name", ["attn_d64_fp16_nc", "attn_d64_fp16_c", "attn_d128_fp16_nc_ragged"])
+@pytest.mark.parametrize("name", ["attn_d64_fp16_nc", "attn_d64_fp16_c", "attn_d128_fp16_nc_ragged", "attn_xattn_d96_bf16"])
 def test_triton_attention_path(name):
     z = np.load(f"{G}/{name}.npz")
     dt = _dtype(z["dtype"])
     q, k, v, o_ref = (_t(z[n], dt) for n in ("q", "k", "v", "o"))
     o, lse = O.sageattn_qk_int8_pv_fp16_triton(q, k, v, is_causal=bool(z["causal"]), return_lse=True)
-    # tl.dot(out_dtype=fp16) accumulation order inside the interpreter is not specified: 2e-3 slack
-    assert (o.float() - o_ref.float()).abs().max().item() < 2e-3
+    # tl.dot(out_dtype=fp16) accumulation order inside the interpreter is not specified: 2e-3 slack; a bf16 output (ulp 2^-7
+    # for 1 <= |o| < 2) turns such a difference into one output ulp
+    tol = 2e-3 if dt == torch.float16 else 2.0 ** -7 + 1e-6
+    assert (o.float() - o_ref.float()).abs().max().item() <= tol
     assert np.allclose(lse.numpy(), z["lse"], atol=2e-4, rtol=1e-5)
     # yard-stick: both are within the reference's own error of exact attention
     exact = O.sdpa_fp32(q, k, v, is_causal=bool(z["causal"]))
