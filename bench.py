@@ -277,9 +277,11 @@ def run_ours(args):
                 "peak_source": f"2 x bf16_tflops ({pk['bf16_tflops']}) of {pk_src} MEASURED_PEAKS.json",
                 "algorithmic_flops_per_launch": total_flops,
                 "algorithmic_hbm_bytes_per_launch": 5.0 * B * H * S * D}
-        tr = os.path.join(ROOT, "profiles", "r01_attn_traffic.json")
-        if os.path.exists(tr):
-            roof["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+        import glob
+        trs = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_attn_traffic.json")))   # newest round's ncu --set full capture
+        if trs:
+            roof["traffic"] = json.load(open(trs[-1])).get("dram_bytes_per_launch")
+            roof["traffic_source"] = os.path.relpath(trs[-1], ROOT)
 
         # ---- e2e: pinned host q,k,v -> H2D -> sageattn -> D2H of o, all inside the timed region
         qh, kh, vh = (torch.randn(B, H, S, D, dtype=dtype).pin_memory() for _ in range(3))
