@@ -30,11 +30,14 @@ VARIANTS = {
 }
 # attn_alt.cu (two softmax warpgroups on alternate key tiles) is selected at run time, on any library
 ENVS = {
+    "alt_wd": {"SAB_ATTN_KERNEL": "alt"},
     "alt": {"SAB_ATTN_KERNEL": "alt"},
     "alt_tau3": {"SAB_ATTN_KERNEL": "alt"},
     "alt_tau3_poly1": {"SAB_ATTN_KERNEL": "alt"},
 }
 VARIANTS.update({
+    # watchdog build first: a wait that never completes reports itself (block 0) and is abandoned instead of hanging the GPU
+    "alt_wd": (["SAB_WATCHDOG"], "attn_alt.cu with bounded mbarrier waits (attn_common.cuh mbar_wait_wd): run BEFORE the other alt variants"),
     "alt": ([], "attn_alt.cu with the exact max rule (in-line O rescale in most tiles)"),
     "alt_tau3": (["SAB_ALT_TAU=3"], "attn_alt.cu with the lazy max (tau = 3)"),
     "alt_tau3_poly1": (["SAB_ALT_TAU=3", "SAB_POLY_EXP_PAIRS=1"], "attn_alt.cu, lazy max, 25 % polynomial exp2"),
@@ -55,7 +58,11 @@ def build():
 def run(names):
     libdir = os.path.join(ROOT, "sageattention_b200", "lib")
     todo = [("product", None)] + [(n, os.path.join(libdir, f"libsab_{n}.so")) for n in (names or VARIANTS)]
+    alt_ok = True
     for name, lib in todo:
+        if name.startswith("alt") and name != "alt_wd" and not alt_ok:
+            print(f"== {name}: skipped (alt_wd did not pass)", flush=True)
+            continue
         if lib is not None and not os.path.exists(lib):
             print(f"== {name}: {lib} not built (python tools/ab_variants.py build)", flush=True)
             continue
@@ -71,10 +78,14 @@ def run(names):
                 r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=tmo)
                 tail = (r.stdout.strip().splitlines() or [""])[-1]
                 print(f"   {what:6s} rc={r.returncode}: {tail}", flush=True)
+                if name == "alt_wd" and (r.returncode != 0 or "mbarrier timeout" in r.stdout + r.stderr):
+                    alt_ok = False
                 if r.returncode != 0:
                     print("   " + "\n   ".join((r.stdout + r.stderr).strip().splitlines()[-12:]), flush=True)
             except subprocess.TimeoutExpired:
                 print(f"   {what:6s} TIMEOUT after {tmo} s (variant hangs?)", flush=True)
+                if name == "alt_wd":
+                    alt_ok = False
                 break
 
 
