@@ -1,6 +1,7 @@
 """A/B harness for opt-in kernel experiments (compile-time variants of csrc/attn.cu next to the product library).
 
-  python tools/ab_variants.py build            # here (CPU box): nvcc every variant into sageattention_b200/lib/libsab_<name>.so
+  python tools/ab_variants.py build [names...] # here (CPU box): nvcc the variants (default: all, 23 MB each — they travel with
+                                               # the gpurun snapshot, so build only what the call will run) into lib/libsab_<name>.so
   python tools/ab_variants.py run [names...]   # on the GPU box: for the product library and each variant, the attention
                                                # parity tests + kernel-only timing (tools/perf_kernel.py), each in its own
                                                # subprocess under a timeout (a hanging variant costs 120 s, not the box)
@@ -45,9 +46,11 @@ VARIANTS.update({
 PARITY_K = "attention_vs_oracle or full_size_config1 or api_behaviour"
 
 
-def build():
+def build(names=()):
     from sageattention_b200 import build as b
     for name, (defs, what) in VARIANTS.items():
+        if names and name not in names:
+            continue
         t0 = time.time()
         if not defs:      # run-time variant of the product library: build it as a variant all the same (one path in run())
             defs = ["SAB_VARIANT_TAG=1"]
@@ -91,7 +94,7 @@ def run(names):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "build":
-        build()
+        build(sys.argv[2:])
     elif len(sys.argv) > 1 and sys.argv[1] == "run":
         run(sys.argv[2:])
     else:
