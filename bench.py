@@ -51,10 +51,10 @@ class ClockSampler:
 
     def start(self):
         try:
-            import shutil
-            pre = ["stdbuf", "-oL"] if shutil.which("stdbuf") else []
-            self.proc = subprocess.Popen(pre + ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                                                "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            # same invocation as the runs that produced samples before (rows carry nvidia-smi's own timestamps, so late
+            # delivery through the pipe does not matter)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
             self.proc = None
