@@ -4,6 +4,7 @@ Recipe (no reference build system is run; no reference source is copied):
   nvcc (flags of /root/reference/setup.py:52-61) on
     /root/reference/csrc/fused/fused.cu                                             -> ref_fused.so
     /root/reference/csrc/qattn/sm89_qk_int8_sv_f8_accum_f{16,32}_fuse_v_scale_attn_inst_buf.cu -> ref_qattn.so
+    /root/reference/csrc/qattn/qk_int_sv_f16_cuda_sm80.cu                           -> ref_qattn80.so
   each linked with a small pybind TU of ours (ref_bind_*.cpp).
 Outputs go only to oracle/_ref/ (git-ignored, travels to the GPU box with gpurun).
 Usage: python oracle/build_ref.py   (needs /root/reference; ~4 min on 8 cores)
@@ -49,6 +50,8 @@ def build():
         "ref_qattn": ([f"{REF}/csrc/qattn/sm89_qk_int8_sv_f8_accum_f16_fuse_v_scale_attn_inst_buf.cu",
                        f"{REF}/csrc/qattn/sm89_qk_int8_sv_f8_accum_f32_fuse_v_scale_attn_inst_buf.cu"],
                       f"{HERE}/ref_bind_qattn.cpp"),
+        # the FP16-PV kernels behind sageattn_qk_int8_pv_fp16_cuda (one TU, ~10 min of nvcc)
+        "ref_qattn80": ([f"{REF}/csrc/qattn/qk_int_sv_f16_cuda_sm80.cu"], f"{HERE}/ref_bind_qattn80.cpp"),
     }
     jobs = []
     for name, (cus, bind) in mods.items():

@@ -16,7 +16,7 @@ Pinning status
     TRITON_INTERPRET=1; fixtures and generator: tests/golden/make_golden.py, tests/golden/*.npz.
   - CUDA-semantics functions (``quant_int8_cuda``, ``per_channel_fp8_cuda``, ``attn_int8_fp8_cuda``)
     are checked on the GPU box against the real reference kernels built for sm_100a into
-    oracle/_ref/ (oracle/build_ref.py) by tests/test_gpu_vs_reference.py.
+    oracle/_ref/ (oracle/build_ref.py) by tests/test_gpu_parity.py.
 """
 from __future__ import annotations
 
@@ -403,6 +403,78 @@ def sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout="HND", is_causal=False,
     if return_lse:
         o, lse = o
         lse = lse / LOG2E_PY + (lse_corr * sm_scale if smooth_k else 0.0)           # core.py:823-826
+    if tensor_layout == "NHD":
+        o = o.transpose(1, 2)
+    o = o[..., :hd_og]
+    return (o, lse) if return_lse else o
+
+
+def attn_int8_fp16_cuda(q8, k8, v, q_scale, k_scale, *, qk_quant_gran="per_thread", is_causal=False, sm_scale=1.0,
+                        out_dtype=torch.float16, kv_tile=64, return_lse=False):
+    """csrc/qattn/qk_int_sv_f16_cuda_sm80.cu:46-640 (`qk_int_sv_f16_attn_kernel`, the accum_f32 instantiation) restated:
+    the fp8 kernel's loop without the exponent offset and with fp16 P and V —
+      S_f = float(S_i32) * (sm_scale*log2e*q_scale*k_scale)   (:92, 255-300)   masks -5e6 (attn_utils.cuh:296-351)
+      m_new = max(m_old, rowmax(S_f)); P = exp2(S_f - m_new)  (update_mdo<..., exp_offset=false>, :303-307)
+      d += sum(P) in fp32 (accumulate_d kCudaCore, :312); P16 = half(P) (RS_32_to_16, :316)
+      O = O*alpha + P16 @ V16 with f32 accumulators          (compute_fp16_sv_permuted, :339)
+    epilogue O/d -> out dtype, lse = log2(d) + m              (normalize_d :540, :560-640)."""
+    B, Hq, Sq, D = q8.shape
+    _, Hk, Sk, _ = k8.shape
+    g = Hq // Hk
+    qs_row = _expand_q_scale(q_scale, qk_quant_gran, Sq)[:, :, :Sq]
+    ks_key = _expand_k_scale(k_scale, qk_quant_gran, Sk)[:, :, :Sk].repeat_interleave(g, dim=1)
+    kf = k8.float().repeat_interleave(g, dim=1)
+    vf = v.to(torch.float16).float().repeat_interleave(g, dim=1)
+    qf = q8.float()
+    sm2 = torch.tensor(sm_scale, dtype=torch.float32) * torch.tensor(LOG2E_CU, dtype=torch.float32)
+    m = torch.full((B, Hq, Sq), MASK_VALUE, dtype=torch.float32)
+    d = torch.ones((B, Hq, Sq), dtype=torch.float32)
+    O = torch.zeros((B, Hq, Sq, D), dtype=torch.float32)
+    qi = torch.arange(Sq)[:, None]
+    for s0 in range(0, Sk, kv_tile):
+        s1 = min(s0 + kv_tile, Sk)
+        if is_causal and s0 > Sq - 1:
+            break
+        S = (qf @ kf[:, :, s0:s1].transpose(-1, -2)) * ((sm2 * qs_row)[..., None] * ks_key[:, :, None, s0:s1])
+        if is_causal:
+            S = torch.where(torch.arange(s0, s1)[None, :] > qi, torch.tensor(MASK_VALUE), S)
+        m_new = torch.maximum(m, S.amax(dim=-1))
+        alpha = torch.exp2(m - m_new)
+        P = torch.exp2(S - m_new[..., None])
+        d = d * alpha + P.sum(dim=-1)
+        O = O * alpha[..., None] + P.half().float() @ vf[:, :, s0:s1]
+        m = m_new
+    out = (O / d[..., None]).to(out_dtype)
+    if return_lse:
+        return out, torch.log2(d) + m
+    return out
+
+
+def sageattn_qk_int8_pv_fp16_cuda(q, k, v, tensor_layout="HND", is_causal=False, qk_quant_gran="per_thread", sm_scale=None,
+                                  smooth_k=True, return_lse=False):
+    """sageattention/core.py:451-633 end to end (CPU), pv_accum_dtype="fp32" (f32 accumulators, :601-603)."""
+    dtype = q.dtype
+    q, k, v, hd_og = _pad_head_dim(q, k, v)
+    if sm_scale is None:
+        sm_scale = hd_og ** -0.5
+    seq_dim = 1 if tensor_layout == "NHD" else 2
+    km = k.mean(dim=seq_dim, keepdim=True) if smooth_k else None                    # core.py:573
+    lse_corr = None
+    if smooth_k and return_lse:
+        qh, kmh = _to_hnd(q, tensor_layout), _to_hnd(km, tensor_layout)
+        g = qh.shape[1] // kmh.shape[1]
+        lse_corr = torch.matmul(qh, kmh.repeat_interleave(g, dim=1).transpose(2, 3)).squeeze(-1).to(torch.float32)
+    if qk_quant_gran == "per_warp":
+        q8, qs, k8, ks = per_warp_int8_cuda(q, k, km, tensor_layout=tensor_layout)
+    else:
+        q8, qs, k8, ks = quant_per_thread_int8_triton(q, k, km, tensor_layout=tensor_layout)
+    o = attn_int8_fp16_cuda(_to_hnd(q8, tensor_layout), _to_hnd(k8, tensor_layout), _to_hnd(v, tensor_layout), qs, ks,
+                            qk_quant_gran=qk_quant_gran, is_causal=is_causal, sm_scale=sm_scale, out_dtype=dtype,
+                            return_lse=return_lse)
+    lse = None
+    if return_lse:
+        o, lse = o
+        lse = lse / LOG2E_PY + (lse_corr * sm_scale if smooth_k else 0.0)
     if tensor_layout == "NHD":
         o = o.transpose(1, 2)
     o = o[..., :hd_og]

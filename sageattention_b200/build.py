@@ -36,7 +36,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), variant: str =
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    objdir = os.path.join(os.path.dirname(LIB), "obj" + ("_" + variant if variant else ""))
+    # variant objects go outside the repo: the gpurun snapshot (512 MiB cap) carries the .so files only
+    objdir = os.path.join(os.path.dirname(LIB), "obj") if not variant else os.path.join("/tmp", "sab_obj_" + variant)
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):

@@ -191,11 +191,51 @@ def sageattn_qk_int8_pv_fp16_cuda(q, k, v, tensor_layout: str = "HND", is_causal
                                   qk_quant_gran: str = "per_thread", sm_scale: Optional[float] = None,
                                   pv_accum_dtype: str = "fp32", smooth_k: bool = True, smooth_v: bool = False,
                                   return_lse: bool = False, **kwargs: Any):
-    """API shell for sageattention/core.py:451-633 (Ampere FP16-PV entry point), served by the INT8+FP8
-    sm_100a kernel with the 448 V range ("fp32+fp32" numerics)."""
-    return sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout=tensor_layout, is_causal=is_causal,
-                                        qk_quant_gran=qk_quant_gran, sm_scale=sm_scale, pv_accum_dtype="fp32+fp32",
-                                        smooth_k=smooth_k, smooth_v=False, return_lse=return_lse)
+    """sageattention/core.py:451-633 (INT8 QK^T + **FP16** PV) on sm_100a: V and P stay in fp16 — callers pick this entry
+    over the fp8 ones for accuracy — through the FP16-PV kernel variant (tcgen05 kind::f16, fp32 accumulation in TMEM).
+    Q/K quantisation is the reference's per-warp / per-thread INT8 (core.py:590-593; WARPQ is 32 for every mode here: the
+    scale packing is internal to this call).  pv_accum_dtype keeps the reference vocabulary ("fp32", "fp16", "fp16+fp32",
+    core.py:601-617): the B200 tensor core always accumulates PV in fp32, i.e. every mode gets the accuracy of "fp32".
+    smooth_v exists in the reference only to protect the "fp16" accumulator from overflow (core.py:606-610); with fp32
+    accumulation it has nothing to do, so it is accepted and ignored with the reference's warning."""
+    dtype = q.dtype
+    _check_inputs(q, k, v)
+    assert qk_quant_gran in ["per_warp", "per_thread"], "qk_quant_gran must be either 'per_warp' or 'per_thread'."
+    if pv_accum_dtype not in ("fp32", "fp16", "fp16+fp32"):
+        raise ValueError(f"Unsupported pv_accum_dtype: {pv_accum_dtype}")
+    if tensor_layout not in ("NHD", "HND"):
+        raise ValueError(f"Unknown tensor layout: {tensor_layout}")
+    _tensor_layout = 0 if tensor_layout == "NHD" else 1
+    q, k, v, head_dim_og = _pad_head_dim(q, k, v)
+    assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of qkv must be contiguous."
+    if is_causal:
+        seq_dim = 1 if _tensor_layout == 0 else 2
+        assert q.size(seq_dim) == k.size(seq_dim), "qo_len and kv_len must be equal for causal attention."
+    if sm_scale is None:
+        sm_scale = head_dim_og ** -0.5
+    lse_correction = None
+    if smooth_k:
+        km = k_mean(k, tensor_layout)
+        if return_lse:
+            lse_correction = _lse_correction(q, km, tensor_layout)
+    else:
+        km = None
+    if qk_quant_gran == "per_warp":
+        q_int8, q_scale, k_int8, k_scale = per_warp_int8(q, k, km, tensor_layout=tensor_layout, BLKQ=128, WARPQ=32, BLKK=64)
+        gran = SAB_GRAN_PER_WARP
+    else:
+        q_int8, q_scale, k_int8, k_scale = per_thread_int8(q, k, km, tensor_layout=tensor_layout, BLKQ=128, WARPQ=32, BLKK=64, WARPK=64)
+        gran = SAB_GRAN_PER_THREAD
+    if smooth_v:
+        warnings.warn(f"pv_accum_dtype is '{pv_accum_dtype}' (fp32 accumulation on B200), smooth_v will be ignored.")
+    v_t = transpose_v_f16(v, tensor_layout=tensor_layout)       # `v.to(torch.float16)`, core.py:603
+    o = torch.empty(q.size(), dtype=dtype, device=q.device)
+    lse = ops.qk_int8_sv_f16_attn(q_int8, k_int8, v_t, o, q_scale, k_scale, _tensor_layout, 1 if is_causal else 0,
+                                  gran, gran, sm_scale, 0, 1 if return_lse else 0)
+    o = o[..., :head_dim_og]
+    if return_lse:
+        return o, lse / _LOG2E + lse_correction * sm_scale if smooth_k else lse / _LOG2E
+    return o
 
 
 def sageattn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens_q: torch.Tensor,

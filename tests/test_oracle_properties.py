@@ -74,3 +74,20 @@ def test_varlen_equals_per_sequence_dense_calls_given_the_batch_mean():
         qi, ki, vi = (t[s].transpose(0, 1).unsqueeze(0) for t in (q, k - km, v))          # [1,H,L,D], K already smoothed
         oi = O.sageattn_qk_int8_pv_fp16_triton(qi, ki, vi, smooth_k=False)
         assert (o[s].transpose(0, 1).unsqueeze(0).float() - oi.float()).abs().max().item() <= 2e-3, i
+
+
+def test_fp16_pv_cuda_entry_is_more_accurate_than_the_fp8_one_and_respects_causality():
+    """sageattn_qk_int8_pv_fp16_cuda (core.py:451-633): same INT8 QK^T as the fp8 entry but fp16 P and V, so its error against
+    exact attention is the QK quantisation error alone — smaller than the fp8 entry's; causal prefix property; NHD == HND."""
+    q, k, v = _mk(1, 4, 2, 320, 320, 64, seed=7)
+    exact = O.sdpa_fp32(q, k, v)
+    e16 = (O.sageattn_qk_int8_pv_fp16_cuda(q, k, v).float() - exact).abs().mean().item()
+    e8 = (O.sageattn_qk_int8_pv_fp8_cuda(q, k, v).float() - exact).abs().mean().item()
+    assert e16 < e8 and e16 < 5e-3
+    oc, lse = O.sageattn_qk_int8_pv_fp16_cuda(q, k, v, is_causal=True, return_lse=True)
+    assert (oc.float() - O.sdpa_fp32(q, k, v, is_causal=True)).abs().max().item() < 3e-2
+    assert oc.shape == q.shape and lse.shape == q.shape[:3]
+    on = O.sageattn_qk_int8_pv_fp16_cuda(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), tensor_layout="NHD", is_causal=True)
+    assert torch.equal(on.transpose(1, 2), oc)
+    ow = O.sageattn_qk_int8_pv_fp16_cuda(q, k, v, qk_quant_gran="per_warp")
+    assert (ow.float() - exact).abs().mean().item() < 8e-3

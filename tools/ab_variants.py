@@ -10,7 +10,7 @@ The product library is never replaced: a variant is selected per process with SA
 Variants whose P is not bit-identical to the reference kernel (polynomial exp2) run the parity tests with the tolerance
 tests already state against the oracle (5e-3); the bit-exactness tests of S / P / m / d are expected to fail for them and
 are excluded by -k."""
-import os, subprocess, sys, time
+import os, re, subprocess, sys, time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -58,10 +58,21 @@ def build(names=()):
         print(f"[build] {name:16s} {time.time() - t0:5.1f} s  {lib}  ({what})", flush=True)
 
 
-def run(names):
+def _sub(cmd, env, tmo):
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=tmo)
+        return r.returncode, r.stdout, r.stderr
+    except subprocess.TimeoutExpired:
+        return None, "", ""
+
+
+def run(names, top_k=3):
+    """Kernel timing for every variant first (cheap), then the parity subset only for the product and the top_k fastest
+    variants (by the first shape: hd128 S=8192 non-causal per-thread)."""
     libdir = os.path.join(ROOT, "sageattention_b200", "lib")
     todo = [("product", None)] + [(n, os.path.join(libdir, f"libsab_{n}.so")) for n in (names or VARIANTS)]
     alt_ok = True
+    score, envs = {}, {}
     for name, lib in todo:
         if name.startswith("alt") and name != "alt_wd" and not alt_ok:
             print(f"== {name}: skipped (alt_wd did not pass)", flush=True)
@@ -73,23 +84,31 @@ def run(names):
         if lib:
             env["SAB_LIB_PATH"] = lib
         env.update(ENVS.get(name, {}))
-        print(f"== {name}", flush=True)
-        for what, cmd, tmo in (("parity", [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
-                                            "-k", PARITY_K, "-p", "no:cacheprovider"], 180),
-                               ("perf", [sys.executable, os.path.join(ROOT, "tools", "perf_kernel.py")], 120)):
-            try:
-                r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=tmo)
-                tail = (r.stdout.strip().splitlines() or [""])[-1]
-                print(f"   {what:6s} rc={r.returncode}: {tail}", flush=True)
-                if name == "alt_wd" and (r.returncode != 0 or "mbarrier timeout" in r.stdout + r.stderr):
-                    alt_ok = False
-                if r.returncode != 0:
-                    print("   " + "\n   ".join((r.stdout + r.stderr).strip().splitlines()[-12:]), flush=True)
-            except subprocess.TimeoutExpired:
-                print(f"   {what:6s} TIMEOUT after {tmo} s (variant hangs?)", flush=True)
-                if name == "alt_wd":
-                    alt_ok = False
-                break
+        envs[name] = env
+        rc, out, err = _sub([sys.executable, os.path.join(ROOT, "tools", "perf_kernel.py")], env, 150)
+        if rc is None:
+            print(f"== {name}: perf TIMEOUT (variant hangs?)", flush=True)
+            if name == "alt_wd":
+                alt_ok = False
+            continue
+        tail = (out.strip().splitlines() or [""])[-1]
+        print(f"== {name}: perf rc={rc}: {tail}", flush=True)
+        if name == "alt_wd" and (rc != 0 or "mbarrier timeout" in out + err):
+            alt_ok = False
+        if rc != 0:
+            print("   " + "\n   ".join((out + err).strip().splitlines()[-12:]), flush=True)
+            continue
+        m = re.search(r"per_thread: (\d+)", tail)
+        if m and name != "alt_wd":
+            score[name] = int(m.group(1))
+    best = sorted((n for n in score if n != "product"), key=lambda n: -score[n])[:top_k]
+    for name in ["product"] + best:
+        rc, out, err = _sub([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
+                             "-k", PARITY_K, "-p", "no:cacheprovider"], envs[name], 240)
+        tail = (out.strip().splitlines() or [""])[-1] if rc is not None else "TIMEOUT"
+        print(f"== {name}: parity rc={rc}: {tail}", flush=True)
+        if rc not in (0, None):
+            print("   " + "\n   ".join((out + err).strip().splitlines()[-25:]), flush=True)
 
 
 if __name__ == "__main__":
