@@ -10,7 +10,7 @@ N = 1  workload = BASELINE.json configs[1]: qk_int8_pv_fp8, hd=128, seq=8192, no
        (the public `sageattn()` call).  `value`  : attention TFLOPS (4*B*H*S^2*D / t) with q,k,v resident in HBM.
        `roofline`: the dominant kernel (sage_attn_fwd_kernel) alone, CUDA events on the launch stream.
        `e2e`     : same metric through the public API from PINNED HOST buffers, H2D of q,k,v and D2H of o timed.
-N > 1  workload = configs[4]: sequence-parallel sageattn, hd=128, seq=32768, B=1 H=32, Q rows sharded over ranks,
+N > 1  workload = configs[4]: sequence-parallel sageattn, hd=128, seq=32768, B=1 H=30, Q rows sharded over ranks,
        INT8 K / FP8 V all-gathered over NCCL (sageattention_b200.parallel); total work fixed -> "scaling": "strong".
 --impl reference : the reference's own algorithm on the HOST cores (CPU port in oracle/, all torch threads) on a
        bounded sample of the same workload; rank 0 only.
@@ -28,6 +28,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the context block (other configs, reference CUDA kernels on this GPU)")
     return ap.parse_args()
 
 
@@ -108,7 +109,7 @@ WORKLOAD_N1 = "configs[1]: qk_int8_pv_fp8 hd=128 seq=8192 causal=False B=4 H=32 
 
 
 def workload_sp(world):
-    return (f"configs[4]: sequence-parallel sageattn hd=128 seq=32768 B=1 H=32 non-causal, Q rows sharded over {world} ranks, "
+    return (f"configs[4]: sequence-parallel sageattn hd=128 seq=32768 B=1 H=30 (example/parallel_sageattn_cogvideo.py:32) non-causal, Q rows sharded over {world} ranks, "
             "INT8 K / FP8 V all-gathered over NCCL")
 
 
@@ -125,7 +126,7 @@ def run_reference(args):
         B, H, S, full = 1, 8, 8192, (4, 32, 8192)
         workload = WORKLOAD_N1
     else:
-        B, H, S, full = 1, 1, 32768, (1, 32, 32768)
+        B, H, S, full = 1, 1, 32768, (1, 30, 32768)
         workload = workload_sp(args.gpus)
     torch.manual_seed(0)
     q, k, v = (torch.randn(B, H, S, D).to(torch.bfloat16) for _ in range(3))
@@ -165,6 +166,103 @@ def time_events(fn, steps, stream=None):
     return e0.elapsed_time(e1) / steps  # ms
 
 
+def _time_fn(fn, n, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    return time_events(fn, n)
+
+
+def sweep_configs(dev, dtype):
+    """Kernel-only and whole-call TFLOP/s of the other BASELINE.json configs and of the seq 8K-32K target range (context for the
+    headline; the timed step above stays configs[1]).  Each entry: CUDA events, 2 warm-ups, few repeats (inputs >> L2)."""
+    import torch
+    import sageattention_b200 as sab
+    from sageattention_b200 import ops
+    out = {}
+
+    def dense(name, B, H, S, D, causal, n):
+        q, k, v = (torch.randn(B, H, S, D, device=dev, dtype=dtype) for _ in range(3))
+        km = sab.k_mean(k)
+        q8, qs, k8, ks = sab.per_thread_int8(q, k, km)
+        v8, vs, _ = sab.per_channel_fp8(v, scale_max=2.25, smooth_v=False)
+        o = torch.empty_like(q)
+        kern = lambda: ops.qk_int8_sv_f8_attn(q8, k8, v8, o, qs, ks, vs, None, 1, int(causal), 3, 3, D ** -0.5, 0, 0)
+        call = lambda: sab.sageattn(q, k, v, tensor_layout="HND", is_causal=causal)
+        fl = flops(B, H, S, S, D, causal)
+        kms, cms = _time_fn(kern, n), _time_fn(call, n)
+        out[name] = {"B": B, "H": H, "S": S, "D": D, "causal": causal, "kernel_tflops": fl / kms / 1e9, "call_tflops": fl / cms / 1e9,
+                     "kernel_ms": kms, "call_ms": cms}
+        del q, k, v, q8, k8, v8, o
+        torch.cuda.empty_cache()
+
+    for S, n in ((8192, 10), (16384, 5), (32768, 3)):
+        for causal in (False, True):
+            dense(f"hd128_s{S // 1024}k_{'causal' if causal else 'noncausal'}", 4, 32, S, 128, causal, n)
+    dense("configs[2]_hd64_s32k_causal_per_thread", 4, 32, 32768, 64, True, 3)
+    dense("hd64_s8k_noncausal", 4, 32, 8192, 64, False, 10)
+    # configs[3]: sageattn_varlen, GQA Hq=32 / Hkv=8, hd=128, sequence lengths 512..16384 shuffled with seed 0 (SURVEY 8d)
+    lens = [512, 1024, 2048, 4096, 8192, 16384]
+    g = torch.Generator().manual_seed(0)
+    lens = [lens[i] for i in torch.randperm(len(lens), generator=g).tolist()]
+    cu = torch.tensor([0] + torch.tensor(lens).cumsum(0).tolist(), dtype=torch.int32, device=dev)
+    T = int(cu[-1])
+    q = torch.randn(T, 32, 128, device=dev, dtype=dtype)
+    k = torch.randn(T, 8, 128, device=dev, dtype=dtype)
+    v = torch.randn(T, 8, 128, device=dev, dtype=dtype)
+    for causal in (False, True):
+        call = lambda: sab.sageattn_varlen(q, k, v, cu, cu, max(lens), max(lens), is_causal=causal)
+        cms = _time_fn(call, 10)
+        fl = sum(4.0 * 32 * L * L * 128 for L in lens) / (2 if causal else 1)
+        out[f"configs[3]_varlen_gqa_{'causal' if causal else 'noncausal'}"] = {"Hq": 32, "Hkv": 8, "D": 128, "seqlens": lens, "causal": causal,
+                                                                            "call_tflops": fl / cms / 1e9, "call_ms": cms}
+    return out
+
+
+def reference_cuda_on_this_gpu(dev, dtype, B, H, S, D):
+    """Context only: the reference's OWN CUDA kernels (csrc/fused/fused.cu + the sm89 mma.sync attention
+    kernel, compiled unmodified for sm_100a by oracle/build_ref.py into oracle/_ref/) timed on this GPU at configs[1]:
+    kernel-only (reference convention, bench/bench_qk_int8_pv_fp8_cuda.py:66-104) and quantisation + kernel.  The reference's
+    sageattn() raises on sm_100 (core.py:157), so its two stages are called the way core.py:773-819 calls them."""
+    import importlib.util
+    import torch
+
+    def _ref(name):
+        p = os.path.join(ROOT, "oracle", "_ref", name + ".so")
+        if not os.path.exists(p):
+            return None
+        spec = importlib.util.spec_from_file_location(name, p)
+        m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m); return m
+    rf, ra = _ref("ref_fused"), _ref("ref_qattn")
+    if rf is None or ra is None:
+        return {"unavailable": "oracle/_ref/*.so not built"}
+    q, k, v = (torch.randn(B, H, S, D, device=dev, dtype=dtype) for _ in range(3))
+    sm = D ** -0.5
+    q8, k8 = torch.empty(q.shape, dtype=torch.int8, device=dev), torch.empty(k.shape, dtype=torch.int8, device=dev)
+    qs = torch.empty((B, H, S // 128 * 4), dtype=torch.float32, device=dev)
+    ks = torch.empty((B, H, S // 64), dtype=torch.float32, device=dev)
+    vt = torch.empty((B, H, D, S), dtype=dtype, device=dev)
+    v8 = torch.empty(vt.shape, dtype=torch.float8_e4m3fn, device=dev)
+    vs = torch.empty((B, H, D), dtype=torch.float32, device=dev)
+    o = torch.empty_like(q)
+
+    def quant():     # core.py:773-809 with qk_quant_gran="per_warp" (the CUDA quantisers; per_thread is a Triton kernel in the reference)
+        km = k.mean(dim=2, keepdim=True)
+        rf.quant_per_warp_int8_cuda(q, q8, qs, 128, 32, 1)
+        rf.quant_per_block_int8_fuse_sub_mean_cuda(k, km.squeeze(2), k8, ks, 64, 1)
+        rf.transpose_pad_permute_cuda(v, vt, 1)
+        rf.scale_fuse_quant_cuda(vt, v8, vs, S, 2.25, 1)
+    kern = lambda: ra.qk_int8_sv_f8_accum_f16_fuse_v_scale_attn_inst_buf(q8, k8, v8, o, qs, ks, vs, 1, 0, 2, sm, 0)
+    quant()
+    fl = flops(B, H, S, S, D)
+    kms = _time_fn(kern, 5)
+    cms = _time_fn(lambda: (quant(), kern()), 5)
+    return {"what": "thu-ml/SageAttention sm89 kernel (qk_int8_sv_f8_accum_f16_fuse_v_scale_attn_inst_buf, mma.sync) + csrc/fused quantisers, "
+                    "unmodified sources compiled for sm_100a", "workload": "configs[1], per_warp quantisation",
+            "kernel_tflops": fl / kms / 1e9, "quant_plus_kernel_tflops": fl / cms / 1e9, "kernel_ms": kms, "quant_plus_kernel_ms": cms}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -196,7 +294,7 @@ def run_ours(args):
         # SAB_SP_FUSED_GATHER=1: peer copies + per-segment flags inside ONE attention launch instead of the NCCL all-gather
         # before it (sageattention_b200/parallel.py; opt-in until it has been validated on GPUs)
         fused_gather = os.environ.get("SAB_SP_FUSED_GATHER", "0") == "1"
-        B, H, S = 1, 32, 32768
+        B, H, S = 1, 30, 32768      # BASELINE configs[4]: CogVideoX shape of example/parallel_sageattn_cogvideo.py:32 (num_heads = 30)
         assert S % (world * 128) == 0
         Sl = S // world
         workload = workload_sp(world)
@@ -257,6 +355,7 @@ def run_ours(args):
 
     out = None
     cached_kv = None
+    sweep = ref_cuda = same_workload_1gpu = None
     if world == 1:
         # ---- roofline: the dominant kernel alone (pre-quantised operands), CUDA events on the launch stream
         km = sab.k_mean(k)
@@ -318,6 +417,17 @@ def run_ours(args):
         torch.cuda.synchronize()
         cms = time_events(cached, args.steps)
         cached_kv = {"value": total_flops / (cms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": cms}
+        del qh, kh, vh, oh, qd, kd, vd, kvq
+        torch.cuda.empty_cache()
+        if not args.no_sweep:
+            try:
+                sweep = sweep_configs(dev, dtype)
+            except Exception as e:          # context must never take the headline down
+                sweep = {"error": repr(e)}
+            try:
+                ref_cuda = reference_cuda_on_this_gpu(dev, dtype, B, H, S, D)
+            except Exception as e:
+                ref_cuda = {"error": repr(e)}
     else:
         roof = {"bound": "tensor", "achieved": value, "peak": 2.0 * pk["bf16_tflops"] * world, "unit": "TFLOP/s",
                 "frac": value / (2.0 * pk["bf16_tflops"] * world), "traffic": None,
@@ -341,6 +451,21 @@ def run_ours(args):
         nbytes = B * H * Sl * D * 2 * world
         e2e = {"value": total_flops / (ems * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 3 * nbytes,
                "d2h_bytes_per_step": nbytes, "ms_per_step": ems}
+        # the SAME workload (full S=32768 problem) on ONE GPU through the single-GPU call, rank 0, so that a scaling efficiency can
+        # be read off this line alone: value / (world * single_gpu_same_workload.value)
+        if rank == 0 and not args.no_sweep:
+            del sets
+            torch.cuda.empty_cache()
+            fq, fk, fv = (torch.randn(B, H, S, D, device=dev, dtype=dtype) for _ in range(3))
+            one = lambda: sab.sageattn(fq, fk, fv, tensor_layout="HND", is_causal=False)
+            for _ in range(3):
+                one()
+            torch.cuda.synchronize()
+            oms = time_events(one, max(3, min(args.steps, 10)))
+            same_workload_1gpu = {"value": total_flops / (oms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": oms,
+                                  "what": "sageattn() on the full B=1 H=30 S=32768 D=128 problem on one GPU (rank 0), same step definition"}
+            del fq, fk, fv
+        dist.barrier()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -372,6 +497,7 @@ def run_ours(args):
             "roofline": roof, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "cpu_baseline": cpu_baseline,
             "context": {"h100_published_kernel_tops_hd128_8k_noncausal": 900, "cached_kv": cached_kv,
+                        "configs": sweep, "reference_cuda_on_b200": ref_cuda, "single_gpu_same_workload": same_workload_1gpu,
                         "note": "reference publishes kernel-only numbers on other hardware (BASELINE.md); no B200 number exists"},
         }
         print(json.dumps(line))

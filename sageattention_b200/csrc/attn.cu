@@ -1,10 +1,13 @@
-// Fused INT8-QK / FP8-PV attention for sm_100a (B200).
+// Fused INT8-QK attention for sm_100a (B200): the EXACT-max kernel and the FP16-PV variants.
 //
-// One CTA = one 128-row Q tile of one (batch, head).  192 threads, warp-specialised:
-//   warps 0-3 : softmax / correction / epilogue — ONE THREAD PER Q ROW (TMEM lane == row), so row max and
-//               row sum need no shuffles and the O row a thread rescales is the row it owns
-//   warp 4    : TMA producer (Q once; K and V^T in 128-key stages through an NS-deep mbarrier ring, swizzled smem)
-//   warp 5    : tcgen05.mma issuer (single thread) + TMEM allocator
+// Serves (a) the FP16-PV numerics of the reference's Triton kernels (kPV16: sageattn_varlen, sageattn_qk_int8_pv_fp16_triton
+// incl. attn_mask, sageattn_qk_int8_pv_fp16_cuda) and (b) the INT8+FP8 path with the reference's exact running max
+// (SAB_ATTN_KERNEL=exact, debug dumps, head_dim 64 fallback); the product INT8+FP8 kernel at head_dim 128 is attn_lazy.cu.
+// One CTA = one 128-row Q tile of one (batch, head).  384 threads, three warpgroups (setmaxnreg 112 / 80 / 48):
+//   warps 0-3  : softmax / epilogue — ONE THREAD PER Q ROW (TMEM lane == row): row max and row sum need no shuffles
+//   warps 4-7  : correction — rescale this row of O (TMEM) by alpha when the running max moved (alpha through shared memory)
+//   warp 8     : TMA producer (Q once; K and V^T 64-key tiles through an NS-deep mbarrier ring, swizzled smem)
+//   warp 9     : tcgen05.mma issuer (one elected lane) + TMEM allocator;  warps 10-11 idle (setmaxnreg is per warpgroup)
 // The softmax / MMA tile is 64 keys — the reference's CTA_K — so the running-max sequence, P (e4m3) and d are the
 // ones csrc/qattn/qk_int_sv_f8_cuda_sm89.cuh produces.  Tensor memory, 256 columns per CTA (two CTAs per SM):
 //   cols [0,64) / [64,128)  S(j) = Q K_j^T, int32 128x64, kind::i8, DOUBLE-BUFFERED on j&1: QK(j+1), QK(j+2) run on
@@ -656,11 +659,6 @@ static int make_map_u8(CUtensorMap* map, const void* base, uint64_t d0, uint64_t
   return SAB_OK;
 }
 
-// attn_pair.cu
-template <int D, bool kKT, typename OutT>
-int launch_attn_pair(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
-                     cudaStream_t stream);
-
 // attn_hd64.cu: head_dim 64, four CTAs per SM (S single-buffered).  SAB_HD64_KERNEL=2cta falls back to the generic kernel.
 template <bool kKT, typename OutT>
 int launch_attn_hd64(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
@@ -674,38 +672,34 @@ static bool use_hd64_kernel() {
   return v == 1;
 }
 
-// SAB_ATTN_KERNEL=single|pair selects the kernel.  Default: single (one Q tile per CTA, two CTAs per SM) — measured
-// faster on B200 (1.28 vs 1.06 PFLOP/s at hd128 S=8192); pair (attn_pair.cu: two Q tiles per CTA, exp ping-pong) is kept
-// as an experiment: with one warp per scheduler in the exp phase it is latency-bound.
-static int attn_kernel_mode() {   // 0 single, 1 pair, 2 split (attn_split.cu: two softmax threads per row), 3 alt (attn_alt.cu)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SAB_ATTN_KERNEL");
-    v = (e == nullptr) ? 0 : (e[0] == 'p' ? 1 : (e[0] == 's' && e[1] == 'p' ? 2 : (e[0] == 'a' ? 3 : 0)));
-  }
-  return v;
-}
-static bool use_pair_kernel() { return attn_kernel_mode() == 1; }
-
-// attn_split.cu
-template <int D, bool kKT, typename OutT>
-int launch_attn_split(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
-                      cudaStream_t stream);
-
+// attn_lazy.cu: the product kernel of the INT8+FP8 path at head_dim 128 (lazy running max, speculative single-pass softmax).
+template <int D, bool kKT, typename OutT, bool kSeg>
+int launch_attn_lazy(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                     cudaStream_t stream);
 // attn_alt.cu (experiment, hd128 only): two softmax warpgroups on alternate key tiles
 template <int D, bool kKT, typename OutT>
 int launch_attn_alt(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                     cudaStream_t stream);
 
+// SAB_ATTN_KERNEL selects the hd128 INT8+FP8 kernel: (default) lazy = attn_lazy.cu; exact = the kernel of this file, whose
+// P / m / d are bit-identical to the reference kernel's (exact running max, correction warpgroup); alt = attn_alt.cu.
+static int attn_kernel_mode() {   // 0 lazy, 1 exact, 3 alt
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAB_ATTN_KERNEL");
+    v = (e == nullptr) ? 0 : (e[0] == 'e' ? 1 : (e[0] == 'a' ? 3 : 0));
+  }
+  return v;
+}
+
 template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false, bool kSeg = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  if (!kPV16 && !kSeg && use_pair_kernel()) {
-    dim3 g2((grid.x + 1) / 2, grid.y, grid.z);
-    return launch_attn_pair<D, kKT, OutT>(tq, tk, tv, p, g2, stream);
-  }
-  if constexpr (!kPV16 && !kSeg) {
-    if (attn_kernel_mode() == 2 && p.dbg == nullptr) return launch_attn_split<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
+  if constexpr (D == 128 && !kPV16 && !kMask) {
+#ifdef SAB_TIMELINE
+    if (attn_kernel_mode() == 0) return launch_attn_lazy<D, kKT, OutT, kSeg>(tq, tk, tv, p, grid, stream);   // p.dbg carries the timeline
+#endif
+    if (attn_kernel_mode() == 0 && p.dbg == nullptr) return launch_attn_lazy<D, kKT, OutT, kSeg>(tq, tk, tv, p, grid, stream);
   }
   if constexpr (D == 128 && !kPV16 && !kSeg) {
     if (attn_kernel_mode() == 3 && p.dbg == nullptr) return launch_attn_alt<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
@@ -773,11 +767,9 @@ static int attn_entry(int pv16, const int8_t* q_int8, const int8_t* k_int8, cons
 
   CUtensorMap tq, tk, tv;
   const int swqk = D == 128 ? 128 : 64;
-  // box sizes: the single-tile kernel streams 64-key tiles, the paired-tile experiment 128-key stages
-  const bool pairk = !pv16 && use_pair_kernel();
-  const uint32_t kbox = pairk ? LK : BN;
-  const uint32_t vbox = pairk ? LK : (pv16 ? 128 : BN);   // bytes of one V^T row in the box
-  const int swv = pairk ? 128 : (pv16 ? 128 : 64);
+  const uint32_t kbox = BN;                 // 64-key tiles
+  const uint32_t vbox = pv16 ? 128 : BN;    // bytes of one V^T row in the box
+  const int swv = pv16 ? 128 : 64;
   if (kv_seg_len > 0) {
     const int P = Skv / kv_seg_len;
     if ((st = make_map_u8(&tq, q_int8, D, Sq, Hq, B, q_stride_s, q_stride_h, q_stride_b, D, BM, swqk))) return st;

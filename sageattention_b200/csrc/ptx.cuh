@@ -189,6 +189,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                SAB_W4(r, 4), "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0, %1, %2, %3};" ::"r"(a), "r"(b), "r"(c), "r"(d), "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%1], {%0};" ::"r"(v), "r"(taddr) : "memory");
 }
