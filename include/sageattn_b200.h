@@ -131,6 +131,25 @@ int sab_per_channel_fp8(const void* v, int dtype, uint8_t* v_fp8, float* v_scale
                         const int32_t* cu_pad, int nseq, int max_seqlen, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Single-pass front-end ("fuse quantisation into producers").  One launch each; a thread-block
+ * cluster per (b,h) reduces the statistic through distributed shared memory and then quantises, so K / V
+ * are read from HBM once (the second read hits L2) instead of twice:
+ *  sab_k_smooth_quant_int8   = sab_k_mean + sab_quant_per_thread_int8(is_key) [SAB_GRAN_PER_THREAD] or
+ *                              sab_k_mean + sab_quant_per_block_int8(blk 64, SAB_SEM_CUDA) [SAB_GRAN_PER_WARP / PER_BLOCK],
+ *                              i.e. `km = k.mean(...)` + the K half of per_thread_int8 / per_warp_int8
+ *                              (sageattention/core.py:773, 788-795); mean_out [B,H,D] in `dtype` is also returned
+ *                              (needed for the LSE correction, core.py:782-786).  Dense layouts only.
+ *  sab_per_channel_fp8_fused = sab_per_channel_fp8 (dense form) without workspace.
+ * The INT8 / FP8 outputs and scales are bit-identical to the two-step entry points given the same mean.
+ * ---------------------------------------------------------------------------------------------- */
+int sab_k_smooth_quant_int8(const void* k, int dtype, void* mean_out, int8_t* out, float* scale, int B, int H, int S,
+                            int D, int64_t x_stride_b, int64_t x_stride_h, int64_t x_stride_s, int64_t o_stride_b,
+                            int64_t o_stride_h, int64_t o_stride_s, int scale_cols, int granularity, void* stream);
+int sab_per_channel_fp8_fused(const void* v, int dtype, uint8_t* v_fp8, float* v_scale, float* v_mean, int B, int H,
+                              int S, int D, int64_t stride_b, int64_t stride_h, int64_t stride_s, int64_t s_pad,
+                              float scale_max, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Building blocks of the sequence-parallel path (no reference counterpart: the reference ships no SP
  * code; semantics chosen so that the sharded result equals the single-GPU one):
  *  sab_channel_stats   : per-(b,h,d) fp32 sum / max / min over the LOCAL tokens (all-reduced by the host:

@@ -28,6 +28,8 @@ EXPORTS = {
     "sab_per_channel_fp8_workspace_bytes": (c_int64, [c_int] * 4),
     "sab_per_channel_fp8": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_int64] * 4 +
                             [c_float, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sab_k_smooth_quant_int8": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_int64] * 6 + [c_int, c_int, c_void_p]),
+    "sab_per_channel_fp8_fused": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_int64] * 4 + [c_float, c_void_p]),
     "sab_channel_stats": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_int64] * 3 + [c_void_p, c_void_p]),
     "sab_v_quant_with_amax": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_int64] * 4 +
                               [c_float, c_void_p, c_void_p]),

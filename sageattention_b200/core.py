@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from . import ops
 from ._capi import SAB_GRAN_PER_BLOCK, SAB_GRAN_PER_WARP, SAB_GRAN_PER_THREAD
-from .quant import (k_mean, per_block_int8, per_warp_int8, per_thread_int8, per_channel_fp8,
+from .quant import (k_mean, per_block_int8, per_warp_int8, per_thread_int8, per_channel_fp8, quant_q_int8, quant_k_int8, smooth_quant_k,
                     per_block_int8_varlen, per_channel_fp8_varlen, transpose_v_f16, transpose_v_f16_varlen)
 
 _LOG2E = 1.44269504
@@ -81,20 +81,16 @@ def sageattn_qk_int8_pv_fp8_cuda(
     if sm_scale is None:
         sm_scale = head_dim_og ** -0.5
 
+    # front-end: 3 launches (reference: 6 + k.mean, core.py:773-809) — Q quantiser; K mean + K quantiser fused; V statistics + FP8 fused
     lse_correction = None
+    q_int8, q_scale = quant_q_int8(q, qk_quant_gran, tensor_layout)
     if smooth_k:
-        km = k_mean(k, tensor_layout)
+        km, k_int8, k_scale = smooth_quant_k(k, qk_quant_gran, tensor_layout)
         if return_lse:
             lse_correction = _lse_correction(q, km, tensor_layout)
     else:
-        km = None
-
-    if qk_quant_gran == "per_warp":
-        q_int8, q_scale, k_int8, k_scale = per_warp_int8(q, k, km, tensor_layout=tensor_layout, BLKQ=128, WARPQ=32, BLKK=64)
-        gran = SAB_GRAN_PER_WARP
-    else:
-        q_int8, q_scale, k_int8, k_scale = per_thread_int8(q, k, km, tensor_layout=tensor_layout, BLKQ=128, WARPQ=32, BLKK=64, WARPK=64)
-        gran = SAB_GRAN_PER_THREAD
+        k_int8, k_scale = quant_k_int8(k, None, qk_quant_gran, tensor_layout)
+    gran = SAB_GRAN_PER_WARP if qk_quant_gran == "per_warp" else SAB_GRAN_PER_THREAD
 
     o = torch.empty(q.size(), dtype=dtype, device=q.device)
 
@@ -214,18 +210,14 @@ def sageattn_qk_int8_pv_fp16_cuda(q, k, v, tensor_layout: str = "HND", is_causal
     if sm_scale is None:
         sm_scale = head_dim_og ** -0.5
     lse_correction = None
+    q_int8, q_scale = quant_q_int8(q, qk_quant_gran, tensor_layout)
     if smooth_k:
-        km = k_mean(k, tensor_layout)
+        km, k_int8, k_scale = smooth_quant_k(k, qk_quant_gran, tensor_layout)
         if return_lse:
             lse_correction = _lse_correction(q, km, tensor_layout)
     else:
-        km = None
-    if qk_quant_gran == "per_warp":
-        q_int8, q_scale, k_int8, k_scale = per_warp_int8(q, k, km, tensor_layout=tensor_layout, BLKQ=128, WARPQ=32, BLKK=64)
-        gran = SAB_GRAN_PER_WARP
-    else:
-        q_int8, q_scale, k_int8, k_scale = per_thread_int8(q, k, km, tensor_layout=tensor_layout, BLKQ=128, WARPQ=32, BLKK=64, WARPK=64)
-        gran = SAB_GRAN_PER_THREAD
+        k_int8, k_scale = quant_k_int8(k, None, qk_quant_gran, tensor_layout)
+    gran = SAB_GRAN_PER_WARP if qk_quant_gran == "per_warp" else SAB_GRAN_PER_THREAD
     if smooth_v:
         warnings.warn(f"pv_accum_dtype is '{pv_accum_dtype}' (fp32 accumulation on B200), smooth_v will be ignored.")
     v_t = transpose_v_f16(v, tensor_layout=tensor_layout)       # `v.to(torch.float16)`, core.py:603

@@ -33,7 +33,7 @@ constexpr int kLazyThreads = 256;
 #endif
 // A/B switches of the softmax loop (measured on B200)
 #ifndef SAB_LZ_KSPRE      // K dequant scales of tile j+1 fetched during tile j
-#define SAB_LZ_KSPRE 1
+#define SAB_LZ_KSPRE 0
 #endif
 #ifndef SAB_LZ_TESTWAIT   // non-blocking test of s_full(j+1) a few iterations before the prefetch point
 #define SAB_LZ_TESTWAIT 0
@@ -166,9 +166,13 @@ sage_attn_lazy_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             }
           }
           mbar_wait_wd(kv_empty + s, ph ^ 1);
+#ifdef SAB_DBG_NO_TMA     // timing experiment only (results are garbage): the ring turns over without any K/V traffic
+          mbar_arrive(kv_full + s);
+#else
           mbar_expect_tx(kv_full + s, K_TILE + V_TILE);
           tma_load_4d(sK + s * K_TILE, &tmK, kv_full + s, 0, kc, hk, kb);
           tma_load_4d(sV + s * V_TILE, &tmV, kv_full + s, vc, 0, hk, kb);
+#endif
         }
       }
     } else if (warp == 5) {
@@ -189,10 +193,12 @@ sage_attn_lazy_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           }
           const uint64_t dK = dK0 + uint64_t(st) * (K_TILE >> 4);
           const uint32_t tS = tmem_u + (t & 1) * BN;
+#ifndef SAB_DBG_NO_MMA    // timing experiment only: no tensor-core work, the commits still flow
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < D / 32; ++k) umma_i8_ss(tS, dQ + 2 * k, dK + 2 * k, idesc_qk, k > 0);
           }
+#endif
         };
         mbar_wait_wd(q_full, 0);
         issue_qk(0, true);
@@ -214,10 +220,12 @@ sage_attn_lazy_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const int st = j % NS;
           const uint64_t dV = dV0 + uint64_t(st) * (V_TILE >> 4);
           const uint32_t tP = tmem_u + (j & 1) * BN;
+#ifndef SAB_DBG_NO_MMA
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BN / 32; ++k) umma_f8_ts(tmem_u + 128, tP + 8 * k, dV + 2 * k, idesc_pv, (j > 0 || k > 0));
           }
+#endif
           SAB_TL(10);
           if (j + 2 < n_kv) issue_qk(j + 2, false);
           if (elect_one()) {
@@ -255,6 +263,7 @@ sage_attn_lazy_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     // K dequant scales of the NEXT tile are fetched one tile ahead (their L1/L2 latency used to sit at the top of every tile)
     const float* ks_ptr = ks_base + int64_t(k_blk0) * NG * p.ks_stride_idx;
     const int64_t ks_step = int64_t(NG) * p.ks_stride_idx;
+    const bool ks_vec = kKT && p.ks_stride_idx == 1 && (reinterpret_cast<uintptr_t>(ks_ptr) & 15) == 0;
     float coef_cur[NG];
 #pragma unroll
     for (int g = 0; g < NG; ++g) coef_cur[g] = (n_kv > 0 ? ks_ptr[int64_t(g) * p.ks_stride_idx] : 0.f) * qss;
@@ -269,12 +278,23 @@ sage_attn_lazy_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int g = 0; g < NG; ++g) coef[g] = coef_cur[g];
       const bool has_next = j + 1 < n_kv;
       [[maybe_unused]] float ks_next[NG];
+      auto load_ks = [&](int t, float (&dst)[NG]) {   // the NG dequant scales of key tile t (dense per-thread layout: one 16-byte load)
+        if constexpr (kKT) {
+          if (ks_vec) {
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(ks_ptr) + t);
+            dst[0] = v4.x; dst[1] = v4.y; dst[2] = v4.z; dst[3] = v4.w;
+            return;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) dst[g] = __ldg(ks_ptr + t * ks_step + int64_t(g) * p.ks_stride_idx);
+      };
       if constexpr (SAB_LZ_KSPRE != 0) {
-#pragma unroll
-        for (int g = 0; g < NG; ++g) ks_next[g] = has_next ? __ldg(ks_ptr + (j + 1) * ks_step + int64_t(g) * p.ks_stride_idx) : 0.f;
+        if (has_next) load_ks(j + 1, ks_next);
       } else {
+        load_ks(j, coef);
 #pragma unroll
-        for (int g = 0; g < NG; ++g) coef[g] = __ldg(ks_ptr + j * ks_step + int64_t(g) * p.ks_stride_idx) * qss;
+        for (int g = 0; g < NG; ++g) coef[g] *= qss;
       }
       const bool masked_tile = j >= j_mask0;
       bool next_issued = false;
@@ -296,8 +316,10 @@ sage_attn_lazy_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const uint32_t tN = tmem_base + lane_off + ((j + 1) & 1) * BN;
           uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[0]);
           uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[32]);
+#ifndef SAB_DBG_NO_LDTM   // timing experiment only: S is never read (stale registers)
           tmem_ld32(tN, lo);
           tmem_ld32(tN + 32, hi);
+#endif
         }
         next_issued = true;
       };
@@ -342,23 +364,32 @@ sage_attn_lazy_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             } else
 #endif
             {
+#ifdef SAB_DBG_NO_EXP     // timing experiment only: no MUFU
+              e[u] = y0 * 0.001f;
+              e[u + 1] = y1 * 0.001f;
+#else
               e[u] = ex2_approx(y0);
               e[u + 1] = ex2_approx(y1);
+#endif
             }
             if constexpr (MASKED) {
               e[u] = (i < limit) ? e[u] : 0.f;
               e[u + 1] = (i + 1 < limit) ? e[u + 1] : 0.f;
             }
             acc[(w & 1) * 2 + (u >> 1)] = fadd2(acc[(w & 1) * 2 + (u >> 1)], pack_f2(e[u], e[u + 1]));
-            if constexpr (PRE) {   // group g of per-thread K scales = keys {8k+2g, 8k+2g+1}; else four independent chains
-              const int c = kKT ? g : ((i >> 1) & 3);
+            if constexpr (PRE) {   // four independent chains of the running integer maximum
+              const int c = (i >> 1) & 3;
               pm[c] = __vimax3_s32(pm[c], int(s[i]), int(s[i + 1]));
             }
           }
           pk4[w & 3] = pack_e4m3x4(e[0], e[1], e[2], e[3]);
           // P goes out in 4-column pieces as it is produced (short live ranges: tcgen05.st needs consecutive registers).  The
           // speculative pass may do that too: S columns [0,16) — the ones P overwrites — stay in registers for a re-run.
+#ifdef SAB_DBG_NO_STTM    // timing experiment only: P is never written
+          if ((w & 3) == 3) asm volatile("" :: "r"(pk4[0]), "r"(pk4[1]), "r"(pk4[2]), "r"(pk4[3]));
+#else
           if ((w & 3) == 3) tmem_st4(tS + (w >> 2) * 4, pk4[0], pk4[1], pk4[2], pk4[3]);
+#endif
         }
         float a0, a1, a2, a3;
         unpack_f2(fadd2(acc[0], acc[1]), a0, a1);
@@ -384,13 +415,13 @@ sage_attn_lazy_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if constexpr (kKT) viol = (pm[0] > thr[0]) || (pm[1] > thr[1]) || (pm[2] > thr[2]) || (pm[3] > thr[3]);
           else viol = max(max(pm[0], pm[1]), max(pm[2], pm[3])) > thr[0];
         } else {
-          float mx = kMaskValue;
+          // conservative for per-thread K scales: (largest S of the row) x (largest of the four group scales) — may send a tile to
+          // the classic path a little early (the scales of one 64-key block differ by a small factor), never misses an overflow
+          const int v = max(max(pm[0], pm[1]), max(pm[2], pm[3]));
+          float cmax = coef[0];
 #pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            const int v = kKT ? pm[g] : max(max(pm[0], pm[1]), max(pm[2], pm[3]));
-            mx = fmaxf(mx, float(v) * coef[g]);
-          }
-          viol = mx - m > kFp8Offset;
+          for (int g = 1; g < NG; ++g) cmax = fmaxf(cmax, coef[g]);
+          viol = float(v) * cmax - m > kFp8Offset;
         }
         if (!__any_sync(0xffffffffu, viol)) {   // no P above 448 in this warp's 32 rows: commit
           d += sum;

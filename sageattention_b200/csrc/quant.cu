@@ -193,13 +193,13 @@ constexpr int kQfTriton = 1, kQfMean = 2, kQfSmScale = 4;   // FLAGS bits of qua
 //               Triton semantics need trunc(RN(x/scale) + 0.5 sign): equal to n unless y is within 1e-4 of a
 //               half-integer (ties, or the 2.4e-5 error of x*RN(1/scale) against the IEEE quotient could matter);
 //               one |y - n| maximum per 8 elements decides, and those rare rows redo the exact reference sequence.
+// One 128-row tile of one (b,h).  `mean_bh`: the D per-channel means of this (b,h) (global or shared memory), or nullptr.
 template <typename T, int D, int MODE, int FLAGS>
-__global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p) {
+__device__ __forceinline__ void quant_int8_tile(const QuantParams& p, const int tile, const int h, const int b, const T* mean_bh) {
   constexpr bool kTriton = (FLAGS & kQfTriton) != 0, kMean = (FLAGS & kQfMean) != 0, kSms = (FLAGS & kQfSmScale) != 0;
   constexpr int TPR = D / 8;
   constexpr int RPP = 256 / TPR;     // 16 (D=128) / 32 (D=64)
   constexpr int NP = 128 / RPP;      // passes: 8 / 4
-  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
   int S = p.S;
   int64_t x_off, o_off;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p)
   uint64_t nmean2[4];   // (-mean[2w], -mean[2w+1])
   if constexpr (kMean) {
     float mean[8];
-    load8<T>(reinterpret_cast<const T*>(p.mean) + (int64_t(varlen ? 0 : b) * p.H + h) * D + tc * 8, mean);
+    load8<T>(mean_bh + tc * 8, mean);
 #pragma unroll
     for (int w = 0; w < 4; ++w) nmean2[w] = pack2f(-mean[2 * w], -mean[2 * w + 1]);
   }
@@ -401,6 +401,114 @@ __global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p)
   }
 }
 
+template <typename T, int D, int MODE, int FLAGS>
+__global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p) {
+  const int h = blockIdx.y, b = blockIdx.z;
+  const T* mean_bh = nullptr;
+  if constexpr ((FLAGS & kQfMean) != 0) mean_bh = reinterpret_cast<const T*>(p.mean) + (int64_t(p.cu != nullptr ? 0 : b) * p.H + h) * D;
+  quant_int8_tile<T, D, MODE, FLAGS>(p, blockIdx.x, h, b, mean_bh);
+}
+
+// =====================================================================================================
+// Single-pass K path: K smoothing mean + INT8 quantisation in ONE launch.  A thread-block cluster of
+// kKCluster CTAs owns one (b,h) slice; CTA r takes the 128-row tiles r, r+C, ...  Phase 1: per-channel fp32 sums of its tiles
+// -> shared memory; cluster barrier; every CTA folds the C partial sums in rank order through distributed shared memory
+// (identical result in every CTA), rounds the mean to T like `k.mean` (core.py:773) and rank 0 writes it out.  Phase 2: the
+// tiles are quantised with that mean — their second read comes from L2 (the slice was just streamed by this cluster), so
+// HBM sees K once instead of twice (stats pass + quant pass) and two launches disappear.
+// =====================================================================================================
+constexpr int kKCluster = 8;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(const float* local_smem_ptr, uint32_t rank) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local_smem_ptr)), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
+  return v;
+}
+
+// per-channel sums of the 128-row tiles r, r+C, ... of one (b,h): thread (tr, tc) accumulates rows tr, tr+RPP, ... of 8 channels
+template <typename T, int D>
+__device__ __forceinline__ void cluster_channel_sums(const T* base, int64_t ss, int S, int rank, float* s_part /* [D] */) {
+  constexpr int TPR = D / 8, RPP = 256 / TPR;
+  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
+  __shared__ float s_red[RPP][D + 1];
+  float sum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+  const int ntiles = (S + 127) / 128;
+  for (int t = rank; t < ntiles; t += kKCluster) {
+    const int r1 = min(S, (t + 1) * 128);
+#pragma unroll 4
+    for (int r = t * 128 + tr; r < r1; r += RPP) {
+      float f[8];
+      load8<T>(base + int64_t(r) * ss + tc * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum[i] += f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_red[tr][tc * 8 + i] = sum[i];
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float a = 0.f;
+    for (int r = 0; r < RPP; ++r) a += s_red[r][threadIdx.x];
+    s_part[threadIdx.x] = a;
+  }
+}
+
+// The mean alone, with the summation order of the fused kernel below (so that `k_mean` + a quantiser == the fused call, bit for bit).
+template <typename T, int D>
+__global__ void __launch_bounds__(256) k_mean_cluster_kernel(const T* __restrict__ x, T* __restrict__ mean_out, int H, int S, int64_t sb,
+                                                             int64_t sh, int64_t ss) {
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int rank = int(cluster_ctarank());
+  __shared__ float s_part[D];
+  cluster_channel_sums<T, D>(x + int64_t(b) * sb + int64_t(h) * sh, ss, S, rank, s_part);
+  cluster_sync_all();
+  if (rank == 0 && threadIdx.x < D) {
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < kKCluster; ++r) a += ld_dsmem_f32(&s_part[threadIdx.x], uint32_t(r));
+    mean_out[(int64_t(b) * H + h) * D + threadIdx.x] = from_f<T>(__fdiv_rn(a, float(S)));
+  }
+  cluster_sync_all();
+}
+
+template <typename T, int D, int MODE, int FLAGS>
+__global__ void __launch_bounds__(256, 3) k_smooth_quant_kernel(const QuantParams p, T* __restrict__ mean_out) {
+  static_assert((FLAGS & kQfMean) != 0, "the fused K path always subtracts the mean");
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int rank = int(cluster_ctarank());
+  __shared__ float s_part[D];
+  __shared__ __align__(16) T s_mean[D];
+  const T* xb = reinterpret_cast<const T*>(p.x) + int64_t(b) * p.xsb + int64_t(h) * p.xsh;
+  cluster_channel_sums<T, D>(xb, p.xss, p.S, rank, s_part);
+  cluster_sync_all();                      // every CTA's partial sums are visible cluster-wide
+  if (threadIdx.x < D) {
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < kKCluster; ++r) a += ld_dsmem_f32(&s_part[threadIdx.x], uint32_t(r));
+    const T m = from_f<T>(__fdiv_rn(a, float(p.S)));     // torch.mean: fp32 sum / N, cast
+    s_mean[threadIdx.x] = m;
+    if (rank == 0) mean_out[(int64_t(b) * p.H + h) * D + threadIdx.x] = m;
+  }
+  cluster_sync_all();                      // nobody leaves (or reuses s_part) while a peer still reads it; s_mean is complete
+  const int ntiles = (p.S + 127) / 128;
+  for (int t = rank; t < ntiles; t += kKCluster) {
+    quant_int8_tile<T, D, MODE, FLAGS>(p, t, h, b, s_mean);
+    __syncthreads();                       // the tile function's shared scratch is reused by the next tile
+  }
+}
+
 // =====================================================================================================
 // V: per-channel scale, e4m3, transpose to [.., D, S_pad] (token-contiguous).  One CTA = 128 tokens.
 // =====================================================================================================
@@ -410,11 +518,12 @@ struct VQuantParams {
   const int32_t* cu; const int32_t* cu_pad;
 };
 
+// One 128-token tile.  recp_bh / vmean_bh: the D per-channel values of this (b,h) (global or shared memory; vmean may be null).
 template <typename T, int D>
-__global__ void __launch_bounds__(256) v_quant_transpose_kernel(const VQuantParams p) {
+__device__ __forceinline__ void v_quant_transpose_tile(const VQuantParams& p, const int tile, const int h, const int b,
+                                                       const float* recp_bh, const float* vmean_bh) {
   constexpr int TPR = D / 8;
   constexpr int RPP = 256 / TPR;
-  const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   int S = p.S, tok0 = 0;
   int64_t col0 = int64_t(tile) * 128;
   const bool varlen = p.cu != nullptr;
@@ -439,8 +548,8 @@ __global__ void __launch_bounds__(256) v_quant_transpose_kernel(const VQuantPara
   const int bh = (varlen ? 0 : b) * p.H + h;
   for (int task = threadIdx.x; task < D * 4; task += 256) {
     const int d = task % D, seg = task / D;
-    const float recp = p.recp[int64_t(bh) * D + d];      // scale_max / amax
-    const float mean = p.vmean ? p.vmean[int64_t(bh) * D + d] : 0.f;
+    const float recp = recp_bh[d];      // scale_max / amax
+    const float mean = vmean_bh ? vmean_bh[d] : 0.f;
     uint32_t w[8];
 #pragma unroll
     for (int q4 = 0; q4 < 8; ++q4) {
@@ -457,6 +566,85 @@ __global__ void __launch_bounds__(256) v_quant_transpose_kernel(const VQuantPara
     uint8_t* dst = p.out + (int64_t(bh) * D + d) * p.s_pad + col0 + seg * 32;
     reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
     reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) v_quant_transpose_kernel(const VQuantParams p) {
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int64_t bh = int64_t(p.cu != nullptr ? 0 : b) * p.H + h;
+  v_quant_transpose_tile<T, D>(p, blockIdx.x, h, b, p.recp + bh * D, p.vmean ? p.vmean + bh * D : nullptr);
+}
+
+// Single-pass V path: per-channel |max| (+ mean for smooth_v) and the e4m3 quantisation + transpose in ONE launch, same cluster
+// scheme as k_smooth_quant_kernel (max / min are order-independent, so the scales are bit-identical to the two-launch path).
+template <typename T, int D>
+__global__ void __launch_bounds__(256) v_scale_quant_kernel(const VQuantParams p, float* __restrict__ scale_out, float* __restrict__ vmean_out) {
+  constexpr int TPR = D / 8, RPP = 256 / TPR;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int rank = int(cluster_ctarank());
+  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
+  __shared__ float s_red[RPP][D + 1];     // one reduction at a time (the tile function needs 35 KB of the 48 KB static limit)
+  __shared__ float s_part[3][D];          // sum / max / min of this CTA's tiles
+  __shared__ float s_recp[D], s_vmean[D];
+  const T* vb = reinterpret_cast<const T*>(p.v) + int64_t(b) * p.sb + int64_t(h) * p.sh;
+  float sum[8], mx[8], mn[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sum[i] = 0.f; mx[i] = -INFINITY; mn[i] = INFINITY; }
+  const int ntiles = int(p.s_pad / 128);
+  for (int t = rank; t < ntiles; t += kKCluster) {
+    const int r1 = min(p.S, (t + 1) * 128);
+#pragma unroll 4
+    for (int r = t * 128 + tr; r < r1; r += RPP) {
+      float f[8];
+      load8<T>(vb + int64_t(r) * p.ss + tc * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sum[i] += f[i]; mx[i] = fmaxf(mx[i], f[i]); mn[i] = fminf(mn[i], f[i]); }
+    }
+  }
+#pragma unroll
+  for (int q3 = 0; q3 < 3; ++q3) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_red[tr][tc * 8 + i] = q3 == 0 ? sum[i] : (q3 == 1 ? mx[i] : mn[i]);
+    __syncthreads();
+    if (threadIdx.x < D) {
+      float a = q3 == 0 ? 0.f : (q3 == 1 ? -INFINITY : INFINITY);
+      for (int r = 0; r < RPP; ++r) {
+        const float x = s_red[r][threadIdx.x];
+        a = q3 == 0 ? a + x : (q3 == 1 ? fmaxf(a, x) : fminf(a, x));
+      }
+      s_part[q3][threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  cluster_sync_all();
+  if (threadIdx.x < D) {
+    float a = 0.f, m1 = -INFINITY, m2 = INFINITY;
+#pragma unroll
+    for (int r = 0; r < kKCluster; ++r) {
+      a += ld_dsmem_f32(&s_part[0][threadIdx.x], uint32_t(r));
+      m1 = fmaxf(m1, ld_dsmem_f32(&s_part[1][threadIdx.x], uint32_t(r)));
+      m2 = fminf(m2, ld_dsmem_f32(&s_part[2][threadIdx.x], uint32_t(r)));
+    }
+    float amax, mean = 0.f;
+    if (vmean_out) {  // smooth_v: fused.cu:375-386 (mean over the 16-padded length)
+      mean = __fdiv_rn(a, float((p.S + 15) / 16 * 16));
+      amax = fmaxf(fabsf(m1 - mean), fabsf(m2 - mean));
+    } else {
+      amax = fmaxf(fabsf(m1), fabsf(m2));
+    }
+    s_vmean[threadIdx.x] = mean;
+    s_recp[threadIdx.x] = amax > 0.f ? __fdividef(p.scale_max, amax) : 0.f;   // fused.cu:392 (guarded)
+    if (rank == 0) {
+      const int64_t o = (int64_t(b) * p.H + h) * D + threadIdx.x;
+      scale_out[o] = __fdividef(amax, p.scale_max);                          // fused.cu:389
+      if (vmean_out) vmean_out[o] = mean;
+    }
+  }
+  cluster_sync_all();
+  for (int t = rank; t < ntiles; t += kKCluster) {
+    v_quant_transpose_tile<T, D>(p, t, h, b, s_recp, vmean_out ? s_vmean : nullptr);
+    __syncthreads();
   }
 }
 
@@ -554,6 +742,19 @@ static int launch_quant(const QuantParams& p, int dtype, int D, int mode, dim3 g
 
 using namespace sab;
 
+// ---------------------------------------------------------------------------------------------- fused single-pass front-end
+template <typename Kern, typename... Args>
+static int launch_cluster(Kern kern, dim3 grid, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kKCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SAB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, args...));
+  return SAB_OK;
+}
+
 extern "C" int64_t sab_k_mean_workspace_bytes(int B, int H, int S, int D) {
   const int64_t nchunk = (S + kStatChunk - 1) / kStatChunk;
   return int64_t(B) * H * nchunk * 3 * D * sizeof(float);
@@ -566,16 +767,16 @@ extern "C" int sab_k_mean(const void* k, int dtype, void* mean, int B, int H, in
                           int64_t stride_h, int64_t stride_s, void* workspace, void* stream) {
   int st = check_common(k, dtype, D, stride_b, stride_h, stride_s);
   if (st) return st;
-  SAB_REQUIRE(mean && workspace && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_k_mean");
+  SAB_REQUIRE(mean && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_k_mean");
+  (void)workspace;   // kept in the signature (and sized by sab_k_mean_workspace_bytes) for ABI stability; the cluster kernel needs none
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if ((st = run_stats(k, dtype, reinterpret_cast<float*>(workspace), B, H, S, D, stride_b, stride_h, stride_s, s))) return st;
-  const int nchunk = (S + kStatChunk - 1) / kStatChunk;
-  if (dtype == SAB_DTYPE_FP16)
-    channel_stats_stage2<__half><<<B * H, 128, 0, s>>>(reinterpret_cast<float*>(workspace), nchunk, D, S, 0, reinterpret_cast<__half*>(mean), nullptr, nullptr, 0.f, nullptr);
-  else
-    channel_stats_stage2<__nv_bfloat16><<<B * H, 128, 0, s>>>(reinterpret_cast<float*>(workspace), nchunk, D, S, 0, reinterpret_cast<__nv_bfloat16*>(mean), nullptr, nullptr, 0.f, nullptr);
-  SAB_CUDA_OK(cudaGetLastError());
-  return SAB_OK;
+  const dim3 grid(kKCluster, H, B);
+  if (dtype == SAB_DTYPE_FP16) {
+    if (D == 128) return launch_cluster(k_mean_cluster_kernel<__half, 128>, grid, s, reinterpret_cast<const __half*>(k), reinterpret_cast<__half*>(mean), H, S, stride_b, stride_h, stride_s);
+    return launch_cluster(k_mean_cluster_kernel<__half, 64>, grid, s, reinterpret_cast<const __half*>(k), reinterpret_cast<__half*>(mean), H, S, stride_b, stride_h, stride_s);
+  }
+  if (D == 128) return launch_cluster(k_mean_cluster_kernel<__nv_bfloat16, 128>, grid, s, reinterpret_cast<const __nv_bfloat16*>(k), reinterpret_cast<__nv_bfloat16*>(mean), H, S, stride_b, stride_h, stride_s);
+  return launch_cluster(k_mean_cluster_kernel<__nv_bfloat16, 64>, grid, s, reinterpret_cast<const __nv_bfloat16*>(k), reinterpret_cast<__nv_bfloat16*>(mean), H, S, stride_b, stride_h, stride_s);
 }
 
 extern "C" int sab_quant_per_block_int8(const void* x, int dtype, const void* mean, int8_t* out, float* scale, int B,
@@ -730,4 +931,54 @@ extern "C" int sab_v_transpose_f16(const void* v, int dtype, void* v_f16t, int B
 #undef SAB_VT
   SAB_CUDA_OK(cudaGetLastError());
   return SAB_OK;
+}
+
+extern "C" int sab_k_smooth_quant_int8(const void* k, int dtype, void* mean_out, int8_t* out, float* scale, int B, int H, int S,
+                                       int D, int64_t x_stride_b, int64_t x_stride_h, int64_t x_stride_s, int64_t o_stride_b,
+                                       int64_t o_stride_h, int64_t o_stride_s, int scale_cols, int granularity, void* stream) {
+  int st = check_common(k, dtype, D, x_stride_b, x_stride_h, x_stride_s);
+  if (st) return st;
+  SAB_REQUIRE(mean_out && out && scale && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_k_smooth_quant_int8");
+  SAB_REQUIRE(granularity == SAB_GRAN_PER_WARP || granularity == SAB_GRAN_PER_THREAD || granularity == SAB_GRAN_PER_BLOCK, SAB_ERR_INVALID,
+              "unknown granularity %d", granularity);
+  const bool pt = granularity == SAB_GRAN_PER_THREAD;
+  const int need = pt ? (S + 63) / 64 * 4 : (S + 63) / 64;
+  SAB_REQUIRE(scale_cols >= need, SAB_ERR_INVALID, "scale_cols %d < %d", scale_cols, need);
+  SAB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 7) == 0 && o_stride_s % 8 == 0 && o_stride_h % 8 == 0 && o_stride_b % 8 == 0, SAB_ERR_INVALID, "int8 output must be 8-byte aligned");
+  QuantParams p{};
+  p.x = k; p.mean = mean_out; p.out = out; p.scale = scale; p.H = H; p.S = S; p.scale_cols = scale_cols;
+  p.xsb = x_stride_b; p.xsh = x_stride_h; p.xss = x_stride_s; p.osb = o_stride_b; p.osh = o_stride_h; p.oss = o_stride_s;
+  p.blk = 64; p.has_sm_scale = 0; p.sm_scale = 1.f;
+  p.semantics = pt ? SAB_SEM_TRITON : SAB_SEM_CUDA;   // per-thread: quant_per_thread.py semantics; per-warp: csrc/fused/fused.cu
+  p.eps_after = pt ? 1 : 0;
+  const dim3 grid(kKCluster, H, B);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+#define SAB_KF(T, DD)                                                                                                             \
+  do {                                                                                                                            \
+    if (pt) return launch_cluster(k_smooth_quant_kernel<T, DD, kGroupThreadK, kQfTriton | kQfMean>, grid, s, p, reinterpret_cast<T*>(mean_out)); \
+    return launch_cluster(k_smooth_quant_kernel<T, DD, kGroupBlock, kQfMean>, grid, s, p, reinterpret_cast<T*>(mean_out));       \
+  } while (0)
+  if (dtype == SAB_DTYPE_FP16) { if (D == 128) SAB_KF(__half, 128); else SAB_KF(__half, 64); }
+  else { if (D == 128) SAB_KF(__nv_bfloat16, 128); else SAB_KF(__nv_bfloat16, 64); }
+#undef SAB_KF
+}
+
+extern "C" int sab_per_channel_fp8_fused(const void* v, int dtype, uint8_t* v_fp8, float* v_scale, float* v_mean, int B, int H,
+                                         int S, int D, int64_t stride_b, int64_t stride_h, int64_t stride_s, int64_t s_pad,
+                                         float scale_max, void* stream) {
+  int st = check_common(v, dtype, D, stride_b, stride_h, stride_s);
+  if (st) return st;
+  SAB_REQUIRE(v_fp8 && v_scale && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_per_channel_fp8_fused");
+  SAB_REQUIRE(s_pad % 128 == 0 && s_pad >= S && aligned16(v_fp8), SAB_ERR_INVALID, "s_pad must be a multiple of 128, >= S, v_fp8 16-byte aligned");
+  VQuantParams p{};
+  p.v = v; p.out = v_fp8; p.recp = nullptr; p.vmean = nullptr; p.H = H; p.S = S;
+  p.sb = stride_b; p.sh = stride_h; p.ss = stride_s; p.s_pad = s_pad; p.scale_max = scale_max; p.cu = nullptr; p.cu_pad = nullptr;
+  const dim3 grid(kKCluster, H, B);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SAB_DTYPE_FP16) {
+    if (D == 128) return launch_cluster(v_scale_quant_kernel<__half, 128>, grid, s, p, v_scale, v_mean);
+    return launch_cluster(v_scale_quant_kernel<__half, 64>, grid, s, p, v_scale, v_mean);
+  }
+  if (D == 128) return launch_cluster(v_scale_quant_kernel<__nv_bfloat16, 128>, grid, s, p, v_scale, v_mean);
+  return launch_cluster(v_scale_quant_kernel<__nv_bfloat16, 64>, grid, s, p, v_scale, v_mean);
 }

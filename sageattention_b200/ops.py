@@ -55,6 +55,39 @@ def _(k, mean, tensor_layout):
     return None
 
 
+# ----------------------------------------------------------------------------------------------- fused single-pass front-end
+@torch.library.custom_op("sageattention_b200::k_smooth_quant_int8", mutates_args=("mean", "output", "scale"), device_types="cuda")
+def k_smooth_quant_int8(k: torch.Tensor, mean: torch.Tensor, output: torch.Tensor, scale: torch.Tensor, tensor_layout: int,
+                        granularity: int) -> None:
+    """K smoothing mean + INT8 quantisation of K in one launch (cluster per (b,h)); mean [B,H,D] in k.dtype is written too."""
+    B, H, S, D = _bhsd(k, tensor_layout)
+    xs, os_ = _bhs_strides(k, tensor_layout), _bhs_strides(output, tensor_layout)
+    with torch.cuda.device(k.device):
+        check(lib().sab_k_smooth_quant_int8(k.data_ptr(), _dt(k), mean.data_ptr(), output.data_ptr(), scale.data_ptr(), B, H, S, D,
+                                            *xs, *os_, scale.size(-1), granularity, _stream(k)))
+
+
+@k_smooth_quant_int8.register_fake
+def _(k, mean, output, scale, tensor_layout, granularity):
+    return None
+
+
+@torch.library.custom_op("sageattention_b200::per_channel_fp8_fused", mutates_args=("v_fp8", "v_scale", "v_mean"), device_types="cuda")
+def per_channel_fp8_fused(v: torch.Tensor, v_fp8: torch.Tensor, v_scale: torch.Tensor, v_mean: Optional[torch.Tensor],
+                          tensor_layout: int, scale_max: float) -> None:
+    """per_channel_fp8 (dense form) in one launch: per-channel statistics through a cluster reduction, then quantise + transpose."""
+    B, H, S, D = _bhsd(v, tensor_layout)
+    sb, sh, ss = _bhs_strides(v, tensor_layout)
+    with torch.cuda.device(v.device):
+        check(lib().sab_per_channel_fp8_fused(v.data_ptr(), _dt(v), v_fp8.data_ptr(), v_scale.data_ptr(), _ptr(v_mean), B, H, S, D,
+                                              sb, sh, ss, v_fp8.size(-1), float(scale_max), _stream(v)))
+
+
+@per_channel_fp8_fused.register_fake
+def _(v, v_fp8, v_scale, v_mean, tensor_layout, scale_max):
+    return None
+
+
 # ----------------------------------------------------------------------------------------------- INT8 quant
 @torch.library.custom_op("sageattention_b200::quant_per_block_int8", mutates_args=("output", "scale"), device_types="cuda")
 def quant_per_block_int8(input: torch.Tensor, mean: Optional[torch.Tensor], output: torch.Tensor, scale: torch.Tensor,

@@ -55,6 +55,14 @@ def gather_scales(scale_local: torch.Tensor, group=None) -> torch.Tensor:
     return g.permute(1, 2, 0, 3).reshape(B, H, world * n).contiguous()
 
 
+def _chunk_count(n_heads: int, want: int) -> int:
+    """Number of KV-head chunks for the pipelined exchange: the divisor of n_heads closest to `want` (>= 1; e.g. 30 heads, want 4 -> 5... 3)."""
+    if not want or want <= 1:
+        return 1
+    divs = [d for d in range(1, n_heads + 1) if n_heads % d == 0]
+    return min(divs, key=lambda d: (abs(d - want), -d))
+
+
 _COMM_STREAMS = {}
 
 
@@ -161,7 +169,7 @@ def sageattn_sp(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout
     fused = bool(fused_gather) and world > 1
     if fused:
         assert not is_causal, "fused_gather supports non-causal attention only"
-        n_fc = gather_chunks if (gather_chunks and Hk % gather_chunks == 0) else 1
+        n_fc = _chunk_count(Hk, gather_chunks)
         ws = _fused_workspace(group, dev, B, Hk, Sl, D, world, n_fc, rank)
     q_int8 = torch.empty((B, Hq, Sl, D), dtype=torch.int8, device=dev)
     k_int8 = ws.k_local if fused else torch.empty((B, Hk, Sl, D), dtype=torch.int8, device=dev)
@@ -336,6 +344,8 @@ def sageattn_ring(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layo
         if step + 1 < world:                              # pass the slice on while computing with it
             k_nxt, v_nxt = torch.empty_like(k_cur), torch.empty_like(v_cur)
             nxt, prv = (rank + 1) % world, (rank - 1) % world
+            if group is not None:      # P2POp peers are GLOBAL ranks: translate for sub-groups (SP groups inside a DPxSP job)
+                nxt, prv = dist.get_global_rank(group, nxt), dist.get_global_rank(group, prv)
             ops_ = [dist.P2POp(dist.isend, k_cur, nxt, group), dist.P2POp(dist.isend, v_cur, nxt, group),
                     dist.P2POp(dist.irecv, k_nxt, prv, group), dist.P2POp(dist.irecv, v_nxt, prv, group)]
             reqs = dist.batch_isend_irecv(ops_)

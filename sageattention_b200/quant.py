@@ -100,6 +100,27 @@ def quant_k_int8(k: torch.Tensor, km: Optional[torch.Tensor] = None, qk_quant_gr
     return k_int8, k_scale
 
 
+def smooth_quant_k(k: torch.Tensor, qk_quant_gran: str = "per_thread", tensor_layout: str = "HND"):
+    """`km = k.mean(dim=seq, keepdim=True)` (sageattention/core.py:773) + the K half of per_thread_int8 / per_warp_int8 in ONE launch
+    (csrc/quant.cu k_smooth_quant_kernel: a thread-block cluster per (b,h) reduces the mean through distributed shared memory and
+    quantises right away, so K crosses HBM once).  Returns (km, k_int8, k_scale), bit-identical to k_mean() + quant_k_int8()."""
+    from ._capi import SAB_GRAN_PER_WARP, SAB_GRAN_PER_THREAD
+    b, h_kv, kv_len, head_dim = _dims(k, tensor_layout)
+    lay = _layout(tensor_layout)
+    k_int8 = torch.empty(k.shape, dtype=torch.int8, device=k.device)
+    nblk = (kv_len + 63) // 64
+    mean = torch.empty((b, h_kv, head_dim), dtype=k.dtype, device=k.device)
+    if qk_quant_gran == "per_warp":
+        k_scale = torch.empty((b, h_kv, nblk), device=k.device, dtype=torch.float32)
+        gran = SAB_GRAN_PER_WARP
+    else:
+        k_scale = torch.empty((b, h_kv, nblk * 4), device=k.device, dtype=torch.float32)
+        gran = SAB_GRAN_PER_THREAD
+    ops.k_smooth_quant_int8(k, mean, k_int8, k_scale, lay, gran)
+    km = mean.view(b, h_kv, 1, head_dim) if tensor_layout == "HND" else mean.view(b, 1, h_kv, head_dim)
+    return km, k_int8, k_scale
+
+
 def per_warp_int8(q: torch.Tensor, k: torch.Tensor, km: Optional[torch.Tensor] = None, BLKQ: int = 128,
                   WARPQ: int = 32, BLKK: int = 64, tensor_layout: str = "HND"):
     """sageattention/quant.py:105-180: q per WARPQ-row block, k per BLKK block with fused (k - km) in fp32;
@@ -155,7 +176,7 @@ def per_channel_fp8(v: torch.Tensor, tensor_layout: str = "HND", scale_max: floa
     v_fp8 = torch.empty((b, h_kv, head_dim, padded_len), dtype=torch.float8_e4m3fn, device=v.device)
     v_scale = torch.empty((b, h_kv, head_dim), dtype=torch.float32, device=v.device)
     vm = torch.empty((b, h_kv, head_dim), dtype=torch.float32, device=v.device) if smooth_v else None
-    ops.per_channel_fp8(v, v_fp8, v_scale, vm, _layout(tensor_layout), scale_max)
+    ops.per_channel_fp8_fused(v, v_fp8, v_scale, vm, _layout(tensor_layout), scale_max)   # statistics + quantisation in one launch
     return v_fp8, v_scale, vm
 
 

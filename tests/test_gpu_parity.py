@@ -13,6 +13,17 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "tests", "golden")
 TOL_REF = 1e-2      # north-star tolerance vs the reference kernel
+LAZY_TAU = 4        # csrc/attn_lazy.cu SAB_LAZY_TAU: the product kernel's lazy-max threshold (binades)
+
+
+def _kernel_tau(D):
+    """Which running-max rule serves padded head dim D: the product INT8+FP8 kernel at head_dim 128 keeps a LAZY max (it moves only
+    when a P would overflow e4m3; csrc/attn_lazy.cu), head_dim 64 and SAB_ATTN_KERNEL=exact keep the reference's exact max.  The
+    oracle restates both (lazy_tau=...), so the CUDA path is always compared with the oracle run with ITS arithmetic; against the
+    reference kernel (exact max) a lazy-max result is a different e4m3 rounding realisation of the same P — compared statistically."""
+    if os.environ.get("SAB_ATTN_KERNEL", "")[:1] == "e":
+        return None
+    return LAZY_TAU if D > 64 else None
 
 
 def assert_close_ulp(a, b, what=""):
@@ -178,6 +189,34 @@ def test_quant_bit_exact_vs_real_reference_kernels(env):
             assert torch.equal(vs, rs)
 
 
+def test_fused_front_end_is_bit_identical_to_the_two_step_calls(env):
+    """`smooth_quant_k` (K mean + INT8 K in one cluster launch) and the fused `per_channel_fp8` must equal the
+    two-step entry points bit for bit (mean, INT8 / FP8 bytes, scales), for both layouts, granularities, ragged and tiny lengths."""
+    sab, ops, O = env
+    from sageattention_b200.quant import quant_k_int8, smooth_quant_k
+    for (B, Hk, S, D, dt, layout) in [(2, 3, 333, 128, torch.bfloat16, "HND"), (1, 2, 1000, 64, torch.float16, "NHD"), (1, 1, 1, 64, torch.float16, "HND"),
+                                      (1, 4, 8192, 128, torch.bfloat16, "HND"), (2, 2, 130, 128, torch.float16, "NHD")]:
+        _, k, v = _mk(B, Hk, S, D, dt, Hk=Hk)
+        if layout == "NHD":
+            k, v = k.transpose(1, 2).contiguous(), v.transpose(1, 2).contiguous()
+        km = sab.k_mean(k, layout)
+        for gran in ("per_thread", "per_warp"):
+            k8, ks = quant_k_int8(k, km, gran, layout)
+            km2, k8b, ksb = smooth_quant_k(k, gran, layout)
+            assert torch.equal(km2, km) and torch.equal(k8b, k8) and torch.equal(ksb, ks), (B, Hk, S, D, dt, layout, gran)
+        for smax in (448.0, 2.25):
+            for smooth_v in (False, True):
+                v8, vs, vm = sab.per_channel_fp8(v, tensor_layout=layout, scale_max=smax, smooth_v=smooth_v)      # fused
+                r8, rs = torch.empty_like(v8), torch.empty_like(vs)
+                rm = torch.empty_like(vs) if smooth_v else None
+                ops.per_channel_fp8(v, r8, rs, rm, 0 if layout == "NHD" else 1, smax)                              # statistics pass + quantiser
+                if not smooth_v:     # max / min reductions are order-independent: identical scales and bytes
+                    assert torch.equal(v8.view(torch.uint8), r8.view(torch.uint8)) and torch.equal(vs, rs), (B, Hk, S, D, dt, layout, smax)
+                else:                # the V mean is an fp32 sum whose order differs between the two kernels: last-bit differences only
+                    assert torch.allclose(vm, rm, rtol=1e-5, atol=1e-6) and torch.allclose(vs, rs, rtol=1e-5, atol=0)
+                    assert (v8.view(torch.uint8) != r8.view(torch.uint8)).float().mean().item() < 1e-3
+
+
 # ------------------------------------------------------------------------------------------- attention
 CFGS = [
     dict(B=1, H=2, S=320, D=64, dt=torch.float16, causal=False, gran="per_warp", acc="fp32+fp32"),
@@ -198,8 +237,9 @@ def test_attention_vs_oracle(env, c):
     q, k, v = _mk(c["B"], c["H"], c["S"], c["D"], c["dt"], Hk=c.get("Hk"))
     o, lse = sab.sageattn_qk_int8_pv_fp8_cuda(q, k, v, is_causal=c["causal"], qk_quant_gran=c["gran"], pv_accum_dtype=c["acc"], return_lse=True)
     torch.cuda.synchronize()
-    oe, le = O.sageattn_qk_int8_pv_fp8_cuda(q.cpu(), k.cpu(), v.cpu(), is_causal=c["causal"], qk_quant_gran=c["gran"],
-                                            pv_accum_dtype=c["acc"], return_lse=True, emulate_f16_accum=False)
+    tau = _kernel_tau(c["D"])
+    kw = dict(is_causal=c["causal"], qk_quant_gran=c["gran"], pv_accum_dtype=c["acc"], return_lse=True, emulate_f16_accum=False)
+    oe, le = O.sageattn_qk_int8_pv_fp8_cuda(q.cpu(), k.cpu(), v.cpu(), lazy_tau=tau, **kw)     # the kernel's own arithmetic
     assert o.shape == q.shape and o.dtype == q.dtype and lse.shape == q.shape[:3] and lse.dtype == torch.float32
     assert not torch.isnan(o).any()
     # exact exp2 on the CPU vs ex2.approx on the GPU can flip the e4m3 rounding of an isolated P (prob. ~1e-5/element):
@@ -212,18 +252,31 @@ def test_attention_vs_oracle(env, c):
     # lse = kernel lse (agrees to 1e-4 with the reference kernel, test below) + q.km correction computed by torch.matmul in
     # the INPUT dtype (core.py:782-786): cuBLAS vs CPU rounding of that fp16/bf16 product dominates
     assert (lse.cpu() - le).abs().max().item() <= (1e-2 if q.dtype == torch.float16 else 6e-2)
+    if tau is not None:
+        # lazy max vs the reference's exact max: another rounding realisation of the same P, not a less accurate one — the error
+        # against exact fp32 attention must stay at the exact-max arithmetic's level (mean within 10 %, max within 25 % + 2e-3)
+        ox, _ = O.sageattn_qk_int8_pv_fp8_cuda(q.cpu(), k.cpu(), v.cpu(), **kw)
+        sd = O.sdpa_fp32(q.cpu(), k.cpu(), v.cpu(), is_causal=c["causal"])
+        e_k, e_x = (o.cpu().float() - sd).abs(), (ox.float() - sd).abs()
+        assert e_k.mean().item() <= 1.10 * e_x.mean().item() + 1e-4
+        assert e_k.max().item() <= 1.25 * e_x.max().item() + 2e-3
     # NHD layout: same numbers through the other stride set
     qn, kn, vn = (t.transpose(1, 2).contiguous() for t in (q, k, v))
     on = sab.sageattn_qk_int8_pv_fp8_cuda(qn, kn, vn, tensor_layout="NHD", is_causal=c["causal"], qk_quant_gran=c["gran"], pv_accum_dtype=c["acc"])
     assert torch.equal(on.transpose(1, 2), o)
 
 
-def test_attention_vs_real_reference_kernel(env):
-    sab, ops, O = env
+def _check_vs_real_reference_kernel(sab, ops, O):
+    """The CUDA path against the REAL reference sm89 kernels (oracle/_ref, built for sm_100a) on the same quantised operands.
+    Exact-max kernels (head_dim 64, SAB_ATTN_KERNEL=exact): same P / m / d bits as the reference -> <= 4e-3 vs its fp32+fp32 kernel
+    (the residual is the reduced-precision accumulator of the reference's legacy fp8 mma.sync), <= 2e-2 vs its fp32+fp16 kernel (that
+    kernel's own per-tile f16 rounding, attn_utils.cuh:896-974).  Lazy-max kernel (head_dim 128): a different e4m3 rounding realisation
+    of the same P, so the comparison is statistical — mean |diff| <= 2.5e-3, and the error against exact fp32 attention is at the
+    reference kernel's level (mean within 10 %, max within 25 % + 2e-3).  LSE agrees to 5e-4 (log2 units) in every case."""
     rf, ra = _ref("ref_fused"), _ref("ref_qattn")
     if rf is None or ra is None:
-        pytest.skip("oracle/_ref not built")
-    worst = 0.0
+        return None
+    worst, worst_mean = 0.0, 0.0
     for (B, H, S, D, dt, causal, gran) in [(1, 4, 1024, 128, torch.float16, False, "per_warp"), (1, 4, 1024, 64, torch.bfloat16, True, "per_warp"),
                                            (2, 4, 2000, 128, torch.bfloat16, False, "per_thread"), (1, 2, 4096, 128, torch.bfloat16, True, "per_thread"),
                                            (1, 8, 1024, 64, torch.float16, False, "per_thread"), (1, 2, 333, 128, torch.float16, True, "per_thread")]:
@@ -232,6 +285,8 @@ def test_attention_vs_real_reference_kernel(env):
         sm = D ** -0.5
         q8, qs, k8, ks = (sab.per_warp_int8 if gran == "per_warp" else sab.per_thread_int8)(q, k, km)
         g = 2 if gran == "per_warp" else 3
+        tau = _kernel_tau(D)
+        sd = O.sdpa_fp32(q.cpu(), k.cpu(), v.cpu(), is_causal=causal) if tau is not None else None
         for smax, fn in [(2.25, ra.qk_int8_sv_f8_accum_f16_fuse_v_scale_attn_inst_buf), (448.0, ra.qk_int8_sv_f8_accum_f32_fuse_v_scale_attn_inst_buf)]:
             pl = (S + 63) // 64 * 64
             vt = torch.empty((B, H, D, pl), dtype=dt, device="cuda")
@@ -244,19 +299,42 @@ def test_attention_vs_real_reference_kernel(env):
             o = torch.empty_like(q)
             lse = ops.qk_int8_sv_f8_attn(q8, k8, v8, o, qs, ks, vs, None, 1, int(causal), g, g, sm, 0, 1)
             torch.cuda.synchronize()
-            err = (o.float() - o_ref.float()).abs().max().item()
-            worst = max(worst, err)
-            if smax == 448.0:
-                # reference "fp32+fp32" kernel: same P / m / d bits; its legacy fp8 mma.sync accumulates each 64-key
-                # partial product with reduced precision (the reason the reference has a two-level mode at all),
-                # tcgen05 accumulates in full fp32 -> agreement to ~1e-3 relative, far inside the 1e-2 north star
-                assert err <= 4e-3, (B, H, S, D, dt, causal, gran, smax, err)
+            diff = (o.float() - o_ref.float()).abs()
+            err = diff.max().item()
+            worst, worst_mean = max(worst, err), max(worst_mean, diff.mean().item())
+            if tau is None:
+                assert err <= (4e-3 if smax == 448.0 else 2e-2), (B, H, S, D, dt, causal, gran, smax, err)
             else:
-                # reference "fp32+fp16" kernel rounds every 64-key partial product to f16 (attn_utils.cuh:896-974); the
-                # B200 kernel accumulates in fp32 -> the difference IS the reference's f16 rounding (<= 2e-2 here)
-                assert err <= 2e-2, (B, H, S, D, dt, causal, gran, smax, err)
-            assert (lse - lse_ref).abs().max().item() <= 1e-4
-    print(f"worst max-abs vs real reference kernel: {worst:.3e}")
+                assert diff.mean().item() <= 2.5e-3, (B, H, S, D, dt, causal, gran, smax, diff.mean().item())
+                e_k, e_r = (o.cpu().float() - sd).abs(), (o_ref.cpu().float() - sd).abs()
+                assert e_k.mean().item() <= 1.10 * e_r.mean().item() + 1e-4, (B, H, S, D, dt, causal, gran, smax)
+                assert e_k.max().item() <= 1.25 * e_r.max().item() + 2e-3, (B, H, S, D, dt, causal, gran, smax)
+            assert (lse - lse_ref).abs().max().item() <= 5e-4
+    return worst, worst_mean
+
+
+def test_attention_vs_real_reference_kernel(env):
+    sab, ops, O = env
+    r = _check_vs_real_reference_kernel(sab, ops, O)
+    if r is None:
+        pytest.skip("oracle/_ref not built")
+    print(f"worst max-abs / mean-abs vs real reference kernels: {r[0]:.3e} / {r[1]:.3e}")
+
+
+def test_exact_max_kernel_matches_reference_kernel_bits():
+    """SAB_ATTN_KERNEL=exact keeps the reference's exact running max at head_dim 128 as well (csrc/attn.cu): P, m and d are then the
+    reference kernel's, and the output agrees with its fp32+fp32 kernel to 4e-3 (the bound VERDICT r01 asks to keep selectable).
+    The kernel choice is read once per process, so the check runs in a subprocess."""
+    import subprocess, sys
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    env_ = dict(os.environ, SAB_ATTN_KERNEL="exact")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import torch, sageattention_b200 as sab\nfrom sageattention_b200 import ops\nfrom oracle import sage_oracle as O\n"
+            "import test_gpu_parity as T\nr = T._check_vs_real_reference_kernel(sab, ops, O)\nprint('EXACT', r)\n" % (ROOT, os.path.join(ROOT, "tests")))
+    p = subprocess.run([sys.executable, "-c", code], env=env_, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "EXACT" in p.stdout
 
 
 def test_fp16_pv_cuda_entry_vs_real_reference_kernel_and_oracle(env):
@@ -285,7 +363,7 @@ def test_fp16_pv_cuda_entry_vs_real_reference_kernel_and_oracle(env):
             err = (o.float() - o_ref.float()).abs().max().item()
             worst = max(worst, err)
             assert err <= tol, (B, H, S, D, dt, causal, gran, err)
-            assert (lse - lse_ref).abs().max().item() <= 1e-4
+            assert (lse - lse_ref).abs().max().item() <= 5e-4
         oe, le = O.attn_int8_fp16_cuda(q8.cpu(), k8.cpu(), v.cpu(), qs.cpu(), ks.cpu(), qk_quant_gran=gran, is_causal=causal,
                                        sm_scale=sm, out_dtype=dt, return_lse=True)
         assert (o.cpu().float() - oe.float()).abs().max().item() <= tol

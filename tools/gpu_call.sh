@@ -2,5 +2,5 @@
 export PYTHONUNBUFFERED=1
 L=$PWD/sageattention_b200/lib
 mkdir -p gpurun_out
-SAB_ATTN_KERNEL=alt SAB_LIB_PATH=$L/libsab_alt_tau4.so timeout 600 ncu --set full --clock-control none --import-source on -k regex:sage_attn -s 2 -c 1 -f -o gpurun_out/alt4_attn python tools/run_attn_once.py 2 32 8192 128 0 per_thread 3 > gpurun_out/ncu_alt4.log 2>&1; tail -3 gpurun_out/ncu_alt4.log
-SAB_LIB_PATH=$L/libsab_lz_a_p8.so timeout 600 ncu --set full --clock-control none --import-source on -k regex:sage_attn -s 2 -c 1 -f -o gpurun_out/lzp8w_attn python tools/run_attn_once.py 2 32 8192 128 0 per_warp 3 > gpurun_out/ncu_lzp8w.log 2>&1; tail -3 gpurun_out/ncu_lzp8w.log
+for v in t2_base t2_p8 t2_a_p8 t2_a_p6 t2_ad_p12 t2_d_p8; do SAB_LIB_PATH=$L/libsab_$v.so timeout 200 python tools/perf_kernel.py short2 > gpurun_out/perf_$v.log 2>&1; echo "$v: $(tail -1 gpurun_out/perf_$v.log | cut -d' ' -f2-)"; done
+SAB_ATTN_KERNEL=alt SAB_LIB_PATH=$L/libsab_alt_tau4.so timeout 200 python tools/perf_kernel.py short2 > gpurun_out/perf_alt_tau4.log 2>&1; echo "alt_tau4: $(tail -1 gpurun_out/perf_alt_tau4.log | cut -d' ' -f2-)"

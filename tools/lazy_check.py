@@ -7,7 +7,7 @@ import torch
 import sageattention_b200 as sab
 from oracle import sage_oracle as O
 
-tau = None if os.environ.get("SAB_ATTN_KERNEL", "")[:1] == "e" else 3
+tau = None if os.environ.get("SAB_ATTN_KERNEL", "")[:1] == "e" else 4
 worst = 0.0
 for (B, H, Hk, S, D, dt, causal, gran) in [(1, 2, 2, 64, 128, torch.float16, False, "per_thread"), (1, 2, 2, 128, 128, torch.float16, True, "per_warp"),
                                             (1, 2, 1, 320, 128, torch.bfloat16, False, "per_thread"), (2, 4, 2, 200, 128, torch.bfloat16, True, "per_thread"),
