@@ -66,11 +66,8 @@ def quantize_kv(k: torch.Tensor, v: torch.Tensor, tensor_layout: str = "HND", qk
     if pad:
         k, v = F.pad(k, (0, pad)), F.pad(v, (0, pad))
     assert k.stride(-1) == 1 and v.stride(-1) == 1, "Last dim of k, v must be contiguous."
-    if smooth_k:
-        km, k_int8, k_scale = smooth_quant_k(k, qk_quant_gran, tensor_layout)     # mean + INT8 in one launch
-    else:
-        km = None
-        k_int8, k_scale = quant_k_int8(k, None, qk_quant_gran, tensor_layout)
+    km = k_mean(k, tensor_layout) if smooth_k else None
+    k_int8, k_scale = quant_k_int8(k, km, qk_quant_gran, tensor_layout)
     if pv_accum_dtype in ("fp32+fp32", "fp32+fp16") and smooth_v:
         warnings.warn(f"pv_accum_dtype is '{pv_accum_dtype}', smooth_v will be ignored.")
         smooth_v = False

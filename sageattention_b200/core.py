@@ -81,15 +81,14 @@ def sageattn_qk_int8_pv_fp8_cuda(
     if sm_scale is None:
         sm_scale = head_dim_og ** -0.5
 
-    # front-end: 3 launches (reference: 6 + k.mean, core.py:773-809) — Q quantiser; K mean + K quantiser fused; V statistics + FP8 fused
+    # front-end: K mean (2 launches), Q / K quantisers, V statistics (2) + FP8 quantiser — 7 launches (reference: 6 + k.mean, core.py:773-809).
+    # The single-launch cluster variants (quant.smooth_quant_k, per_channel_fp8(fused=True)) exist but measured slower on B200.
     lse_correction = None
+    km = k_mean(k, tensor_layout) if smooth_k else None
+    if smooth_k and return_lse:
+        lse_correction = _lse_correction(q, km, tensor_layout)
     q_int8, q_scale = quant_q_int8(q, qk_quant_gran, tensor_layout)
-    if smooth_k:
-        km, k_int8, k_scale = smooth_quant_k(k, qk_quant_gran, tensor_layout)
-        if return_lse:
-            lse_correction = _lse_correction(q, km, tensor_layout)
-    else:
-        k_int8, k_scale = quant_k_int8(k, None, qk_quant_gran, tensor_layout)
+    k_int8, k_scale = quant_k_int8(k, km, qk_quant_gran, tensor_layout)
     gran = SAB_GRAN_PER_WARP if qk_quant_gran == "per_warp" else SAB_GRAN_PER_THREAD
 
     o = torch.empty(q.size(), dtype=dtype, device=q.device)
@@ -210,13 +209,11 @@ def sageattn_qk_int8_pv_fp16_cuda(q, k, v, tensor_layout: str = "HND", is_causal
     if sm_scale is None:
         sm_scale = head_dim_og ** -0.5
     lse_correction = None
+    km = k_mean(k, tensor_layout) if smooth_k else None
+    if smooth_k and return_lse:
+        lse_correction = _lse_correction(q, km, tensor_layout)
     q_int8, q_scale = quant_q_int8(q, qk_quant_gran, tensor_layout)
-    if smooth_k:
-        km, k_int8, k_scale = smooth_quant_k(k, qk_quant_gran, tensor_layout)
-        if return_lse:
-            lse_correction = _lse_correction(q, km, tensor_layout)
-    else:
-        k_int8, k_scale = quant_k_int8(k, None, qk_quant_gran, tensor_layout)
+    k_int8, k_scale = quant_k_int8(k, km, qk_quant_gran, tensor_layout)
     gran = SAB_GRAN_PER_WARP if qk_quant_gran == "per_warp" else SAB_GRAN_PER_THREAD
     if smooth_v:
         warnings.warn(f"pv_accum_dtype is '{pv_accum_dtype}' (fp32 accumulation on B200), smooth_v will be ignored.")

@@ -2,7 +2,7 @@
 //
 // Serves (a) the FP16-PV numerics of the reference's Triton kernels (kPV16: sageattn_varlen, sageattn_qk_int8_pv_fp16_triton
 // incl. attn_mask, sageattn_qk_int8_pv_fp16_cuda) and (b) the INT8+FP8 path with the reference's exact running max
-// (SAB_ATTN_KERNEL=exact, debug dumps, head_dim 64 fallback); the product INT8+FP8 kernel at head_dim 128 is attn_lazy.cu.
+// (SAB_ATTN_KERNEL=exact, debug dumps, head_dim 64 fallback); the product INT8+FP8 kernel at head_dim 128 is attn_alt.cu.
 // One CTA = one 128-row Q tile of one (batch, head).  384 threads, three warpgroups (setmaxnreg 112 / 80 / 48):
 //   warps 0-3  : softmax / epilogue — ONE THREAD PER Q ROW (TMEM lane == row): row max and row sum need no shuffles
 //   warps 4-7  : correction — rescale this row of O (TMEM) by alpha when the running max moved (alpha through shared memory)
@@ -264,13 +264,6 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     long long* tl = reinterpret_cast<long long*>(p.dbg) + 4096;
 #endif
 
-#ifdef SAB_PREMAX
-    // opt-in build (-DSAB_PREMAX=8|16): the integer row maxima of S(j+1) are gathered in 8/16-column chunks INSIDE the exponential
-    // loop of tile j (issue slots that otherwise wait for the MUFU), so the serial max -> alpha chain of tile j+1 starts
-    // from 4 integers instead of 64.  Only for mask-free tiles whose S buffer is already complete (non-blocking check).
-    int pm[4] = {kIntSentinel, kIntSentinel, kIntSentinel, kIntSentinel};   // kKT: per scale group; else 4 partial chains
-    bool have_pre = false;
-#endif
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t tS = tmem_base + lane_off + (j & 1) * BN;
       // dequant coefficient per scale group of this tile (…sm89.cuh:116-132, 255-257); tile j == 64-key block j
@@ -283,9 +276,6 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && (j + 1) * BN > p.causal_q_offset + qt * BM + 1);
 
       SAB_TL(0);
-#ifdef SAB_PREMAX
-      if (!have_pre)   // otherwise the pre-max pass of the previous iteration saw s_full(j) complete (and fenced)
-#endif
       {
         mbar_wait_wd(s_full + (j & 1), s_parity(j));
         tc_fence_after();
@@ -299,16 +289,6 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld32(tS + 32, hi);
         tc_wait_ld();
       }
-#ifdef SAB_DEFER_PST
-      // opt-in build: the hand-off of P(j-1) (wait::st + fence + arrive, ~130 cycles of the serial chain) is taken here,
-      // after S(j) was waited for and loaded — the store issued at the end of the previous iteration has long landed.
-      // No cycle: s_full(j) depends on p_full(j-2), which was signalled one iteration earlier.
-      if (j > 0) {
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(p_full + ((j - 1) & 1));
-      }
-#endif
       SAB_TL(2);
       if (dump && j == 0) {
 #pragma unroll
@@ -328,9 +308,8 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
 
-      auto tile = [&](auto masked_tag, [[maybe_unused]] auto pre_tag) {
+      auto tile = [&](auto masked_tag) {
         constexpr bool MASKED = decltype(masked_tag)::value;
-        [[maybe_unused]] constexpr bool PRE = decltype(pre_tag)::value;   // SAB_PREMAX builds: gather the maxima of S(j+1) in this tile
         // ---- row max.  Scales are positive, so max_c(S_c*coef_g(c)) = max_g(coef_g * max_{c in g} S_c): integer
         //      max per scale group (DPX 3-input max), one int->float conversion per group instead of per element.
         if constexpr (MASKED) {
@@ -339,17 +318,9 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (i >= limit) s[i] = uint32_t(kIntSentinel);
         }
         float mx = kMaskValue;
-#ifdef SAB_PREMAX
-        const bool use_pre = !MASKED && have_pre;
-#endif
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           int v = kIntSentinel;
-#ifdef SAB_PREMAX
-          if (use_pre) {
-            v = kKT ? pm[g] : max(max(pm[0], pm[1]), max(pm[2], pm[3]));
-          } else
-#endif
           if constexpr (kKT) {
 #pragma unroll
             for (int i8 = 0; i8 < BN; i8 += 8) v = __vimax3_s32(v, int(s[i8 + 2 * g]), int(s[i8 + 2 * g + 1]));
@@ -369,27 +340,14 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mx = fmaxf(mx, c);
         }
         // fp8 P: update_mdo with the -log2(448) offset (attn_utils.cuh:377-396); fp16 P: plain running max (Triton path)
-#ifdef SAB_LAZY_RESCALE
-        // opt-in build (-DSAB_LAZY_RESCALE=tau, log2 units): the running max is only moved when it grew by more than tau;
-        // otherwise P(j) is taken against the stale max (alpha == 1, no O rescale).  The exponent offset shrinks by tau so
-        // that P still fits (0, 448]; e4m3 is a floating format, so P keeps the reference's mantissa bits with a shifted
-        // exponent (elements below 2^(tau-18) of the row maximum flush to zero instead of 2^-18), and d, O and the LSE stay
-        // consistent because they are all relative to the max in use.  With 32 rows per warp and ~1/j chance of a new row
-        // maximum at tile j, the exact rule rescales in ~60 % of the tiles at S=8192; a jump of more than 2^tau is rare.
-        const float m_true = fmaxf(m, kPV16 ? mx : mx - (kFp8Offset - float(SAB_LAZY_RESCALE)));
-        const float m_new = (m_true - m > float(SAB_LAZY_RESCALE)) ? m_true : m;
-#else
         const float m_new = fmaxf(m, kPV16 ? mx : mx - kFp8Offset);
-#endif
         const float alpha = ex2_approx(m - m_new);
         d *= alpha;
         m = m_new;
         // publish alpha: the correction warpgroup rescales this row of O (in TMEM) concurrently with the exponentials.
         // Double-buffered: alpha(j+2) is written only after s_full(j+2), i.e. after the correction warp read alpha(j).
-#ifndef SAB_LATE_ALPHA
         s_alpha[(j & 1) * BM + row] = alpha;
         mbar_arrive(a_full + (j & 1));
-#endif
         const float nm = -m_new;
         SAB_TL(3);
 
@@ -403,21 +361,9 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint64_t nm2 = pack_f2(nm, nm);
         uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
         uint32_t pk[PCOLS];
-#ifdef SAB_PREMAX
-        constexpr int PMW = SAB_PREMAX / 4;   // exp-loop iterations (4 elements each) per pre-max chunk
-        static_assert(SAB_PREMAX == 8 || SAB_PREMAX == 16, "SAB_PREMAX: chunk width 8 or 16 columns");
-        [[maybe_unused]] uint32_t nxt[SAB_PREMAX];
-        [[maybe_unused]] const uint32_t tN = tmem_base + lane_off + ((j + 1) & 1) * BN;
-        if constexpr (PRE) pm[0] = pm[1] = pm[2] = pm[3] = kIntSentinel;   // (the maxima of tile j were consumed above)
-#endif
 #pragma unroll
         for (int w = 0; w < BN / 4; ++w) {
           float e[4];
-#ifdef SAB_PREMAX
-          if constexpr (PRE) {
-            if ((w % PMW) == 0) tmem_ld_chunk(tN + 4 * w, nxt);            // a chunk of S(j+1), in flight under the exps
-          }
-#endif
 #pragma unroll
           for (int u = 0; u < 4; u += 2) {
             const int i = 4 * w + u;
@@ -425,20 +371,8 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint64_t f2 = pack_f2(__int2float_rn(int(s[i])), __int2float_rn(int(s[i + 1])));
             float y0, y1;
             unpack_f2(ffma2(f2, coef2[g], nm2), y0, y1);
-#ifdef SAB_EXP_NO_MUFU
-            e[u] = y0 * 0.001f; e[u + 1] = y1 * 0.001f;
-#elif defined(SAB_POLY_EXP_PAIRS)
-            // opt-in build: SAB_POLY_EXP_PAIRS of every 4 column pairs take the polynomial on the FMA pipe (ptx.cuh)
-            if (((i >> 1) & 3) < SAB_POLY_EXP_PAIRS) {
-              ex2_poly2(y0, y1, e[u], e[u + 1]);
-            } else {
-              e[u] = ex2_approx(y0);
-              e[u + 1] = ex2_approx(y1);
-            }
-#else
             e[u] = ex2_approx(y0);
             e[u + 1] = ex2_approx(y1);
-#endif
             if constexpr (MASKED && kMask) {   // masked-out elements are not a prefix of the tile
               e[u] = (int(s[i]) != kIntSentinel) ? e[u] : 0.f;
               e[u + 1] = (int(s[i + 1]) != kIntSentinel) ? e[u + 1] : 0.f;
@@ -448,37 +382,13 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
             acc[(w & 1) * 2 + (u >> 1)] = fadd2(acc[(w & 1) * 2 + (u >> 1)], pack_f2(e[u], e[u + 1]));
           }
-#ifdef SAB_LATE_ALPHA
-          // opt-in build: alpha = ex2(m - m_new) comes off the MUFU queue behind the other CTA's exponentials; publishing it
-          // (STS + arrive) before the exp loop stalls this in-order warp for that latency.  The correction warps need it
-          // only before PV(j), so it is published after the first 8 exponentials of the tile were issued.
-          if (w == 1) {
-            s_alpha[(j & 1) * BM + row] = alpha;
-            mbar_arrive(a_full + (j & 1));
-          }
-#endif
           if constexpr (kPV16) {
             pk[2 * w] = pack_f16x2(e[0], e[1]);       // p.to(tl.float16), attn_qk_int8_per_block.py:62
             pk[2 * w + 1] = pack_f16x2(e[2], e[3]);
           } else {
             pk[w] = pack_e4m3x4(e[0], e[1], e[2], e[3]);
           }
-#ifdef SAB_PREMAX
-          if constexpr (PRE) {
-            if ((w % PMW) == PMW - 1) {   // the chunk issued 8 / 16 exponentials ago has landed: fold it into the maxima
-              tc_wait_ld();
-#pragma unroll
-              for (int k8 = 0; k8 < SAB_PREMAX; k8 += 8) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) pm[g] = __vimax3_s32(pm[g], int(nxt[k8 + 2 * g]), int(nxt[k8 + 2 * g + 1]));
-              }
-            }
-          }
-#endif
         }
-#ifdef SAB_PREMAX
-        have_pre = PRE;
-#endif
         {
           float a0, a1, a2, a3;
           unpack_f2(fadd2(acc[0], acc[1]), a0, a1);
@@ -526,31 +436,11 @@ sage_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           tmem_st32(tS, pk);
         }
       };
-#ifdef SAB_PREMAX
-      // decide before the tile starts (non-blocking): is S(j+1) complete and mask-free?  Warp-uniform by the vote — the
-      // tcgen05.ld of the chunks is .sync.aligned.  The exp loop of the PRE instantiation is branch-free.
-      bool pre_ok = false;
-      if constexpr (!kMask) {
-        const bool next_masked = (j + 1 >= n_kv) || (kv_len - (j + 1) * BN < BN) ||
-                                 (p.causal && (j + 2) * BN > p.causal_q_offset + qt * BM + 1);
-        if (!masked_tile && !next_masked)
-          pre_ok = __all_sync(0xffffffffu, mbar_test_wait(s_full + ((j + 1) & 1), s_parity(j + 1)));
-        if (pre_ok) tc_fence_after();
-      }
       if (kMask && p.mask_kind == 2) tile_bias();
-      else if (kMask || masked_tile) tile(std::true_type{}, std::false_type{});
-      else if (pre_ok) tile(std::false_type{}, std::true_type{});
-      else tile(std::false_type{}, std::false_type{});
-#else
-      if (kMask && p.mask_kind == 2) tile_bias();
-      else if (kMask || masked_tile) tile(std::true_type{}, std::false_type{});
-      else tile(std::false_type{}, std::false_type{});
-#endif
+      else if (kMask || masked_tile) tile(std::true_type{});
+      else tile(std::false_type{});
 
       SAB_TL(5);
-#ifdef SAB_DEFER_PST
-      if (j == n_kv - 1)   // last tile: nothing to hide the hand-off under
-#endif
       {
         tc_wait_st();
         SAB_TL(6);
@@ -659,8 +549,9 @@ static int make_map_u8(CUtensorMap* map, const void* base, uint64_t d0, uint64_t
   return SAB_OK;
 }
 
-// attn_hd64.cu: head_dim 64, four CTAs per SM (S single-buffered).  SAB_HD64_KERNEL=2cta falls back to the generic kernel.
-template <bool kKT, typename OutT>
+// attn_hd64.cu: head_dim 64, four CTAs per SM (S single-buffered); kLazy selects the lazy / exact running max.
+// SAB_HD64_KERNEL=2cta falls back to the generic kernel of this file.
+template <bool kKT, typename OutT, bool kLazy>
 int launch_attn_hd64(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                      cudaStream_t stream);
 static bool use_hd64_kernel() {
@@ -672,40 +563,33 @@ static bool use_hd64_kernel() {
   return v == 1;
 }
 
-// attn_lazy.cu: the product kernel of the INT8+FP8 path at head_dim 128 (lazy running max, speculative single-pass softmax).
-template <int D, bool kKT, typename OutT, bool kSeg>
-int launch_attn_lazy(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
-                     cudaStream_t stream);
-// attn_alt.cu (experiment, hd128 only): two softmax warpgroups on alternate key tiles
+// attn_alt.cu: the product kernel of the INT8+FP8 path at head_dim 128 — two softmax warpgroups on alternate key tiles, lazy max.
 template <int D, bool kKT, typename OutT>
 int launch_attn_alt(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                     cudaStream_t stream);
 
-// SAB_ATTN_KERNEL selects the hd128 INT8+FP8 kernel: (default) lazy = attn_lazy.cu; exact = the kernel of this file, whose
-// P / m / d are bit-identical to the reference kernel's (exact running max, correction warpgroup); alt = attn_alt.cu.
-static int attn_kernel_mode() {   // 0 lazy, 1 exact, 3 alt
+// SAB_ATTN_KERNEL=exact selects the reference's exact running max everywhere (the kernel of this file at head_dim 128, the exact
+// instantiation of attn_hd64.cu): P / m / d are then bit-identical to the reference kernel's.  Default: the lazy-max product kernels.
+static bool exact_max_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SAB_ATTN_KERNEL");
-    v = (e == nullptr) ? 0 : (e[0] == 'e' ? 1 : (e[0] == 'a' ? 3 : 0));
+    v = (e != nullptr && e[0] == 'e') ? 1 : 0;
   }
-  return v;
+  return v == 1;
 }
 
 template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false, bool kSeg = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  if constexpr (D == 128 && !kPV16 && !kMask) {
-#ifdef SAB_TIMELINE
-    if (attn_kernel_mode() == 0) return launch_attn_lazy<D, kKT, OutT, kSeg>(tq, tk, tv, p, grid, stream);   // p.dbg carries the timeline
-#endif
-    if (attn_kernel_mode() == 0 && p.dbg == nullptr) return launch_attn_lazy<D, kKT, OutT, kSeg>(tq, tk, tv, p, grid, stream);
-  }
   if constexpr (D == 128 && !kPV16 && !kSeg) {
-    if (attn_kernel_mode() == 3 && p.dbg == nullptr) return launch_attn_alt<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
+    if (!exact_max_mode() && p.dbg == nullptr) return launch_attn_alt<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
   }
   if constexpr (D == 64 && !kPV16 && !kSeg) {
-    if (use_hd64_kernel() && p.dbg == nullptr) return launch_attn_hd64<kKT, OutT>(tq, tk, tv, p, grid, stream);
+    if (use_hd64_kernel() && p.dbg == nullptr) {
+      if (exact_max_mode()) return launch_attn_hd64<kKT, OutT, false>(tq, tk, tv, p, grid, stream);
+      return launch_attn_hd64<kKT, OutT, true>(tq, tk, tv, p, grid, stream);
+    }
   }
   constexpr int NS = kPV16 ? ((D == 128) ? 3 : 6) : ((D == 128) ? 5 : 10);
   // Q tile + NS x (K + V^T 64-key tile) + alpha hand-off + barriers (97.5 KB at hd128): two CTAs per SM (TMEM: 2 x 256 columns)

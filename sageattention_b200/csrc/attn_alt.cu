@@ -1,28 +1,33 @@
-// Fused INT8-QK / FP8-PV attention for sm_100a — "alternating-tile" softmax: TWO warpgroups per Q tile, on ALTERNATE key tiles.
-// EXPERIMENT (opt-in: SAB_ATTN_KERNEL=alt), written at the end of round 1 without GPU access: not yet run on a B200.
+// Fused INT8-QK / FP8-PV attention for sm_100a (B200) — the PRODUCT kernel of the INT8+FP8 path at head_dim 128.
 //
-// Same tile pipeline as attn.cu (128-row Q tile per CTA, 64-key tiles, S double-buffered in TMEM, two CTAs per SM,
-// QK0 QK1 | PV0 QK2 | PV1 QK3 ... on the in-order tensor pipe).  attn.cu is bound by the serial chain of ONE softmax warp
-// per 32 rows (wait -> TMEM load -> row max -> alpha -> 64 exponentials -> P store -> hand-off, ~1410 cycles per tile with
-// the co-resident CTA), which leaves the MUFU idle ~40 % of the time.  Here warpgroup 0 takes the even
-// key tiles and warpgroup 1 the odd ones of the SAME 128 rows (warps w and w+4 reach the same TMEM lane quadrant), one thread
-// per row and tile as before, so both S buffers are being consumed at once and every scheduler holds four independent
-// exp chains (two per CTA) instead of two.  The online softmax couples consecutive tiles only through the running max:
-//   m(j) = max(m(j-1), rowmax(S(j)) - 8.807)        one float per row through shared memory + one mbarrier (m_full)
-//   O   *= 2^(m(j-1) - m(j)) before PV(j)             done in-line by the thread that owns tile j (after step(j-1) retired)
-//   d                                                 each warpgroup keeps the sum of ITS tiles relative to its last max;
-//                                                     the two partial sums are combined once in the epilogue
-// so m and P are bit-identical to attn.cu and the reference kernel; d (and hence O) differs by fp32 rounding of the split
-// sum only.  There is no correction warpgroup: 384 threads, registers 96 / 96 / 48 (the split-row kernel's proven budget).
-// -DSAB_ALT_TAU=t (log2 units) makes the max lazy (moves only when it grew by more than t; exponent offset 8.807 - t): the
-// in-line O rescale then happens in a few percent of the tiles instead of most (tests/test_poly_exp_numerics.py).
+// Tile pipeline shared with attn.cu: one 128-row Q tile per CTA, 64-key tiles (the reference's CTA_K), S double-buffered in TMEM,
+// P(j) (e4m3) written over its S buffer and fed to the PV MMA from TMEM, O fp32 in TMEM, two CTAs per SM, in-order tensor pipe
+// QK0 QK1 | PV0 QK2 | PV1 QK3 ...  What differs is the softmax side, shaped by the B200 measurements of round 2:
+//   * MUFU.EX2 runs at 16 lanes/clk/SM (tools/microbench/mufu_rate.cu: 8.0 cycles per warp instruction and sub-partition), so a
+//     128x64 tile costs 512 MUFU cycles against 256 tensor cycles: the exponentials are the roofline of an 8-bit attention kernel,
+//     and what the exact kernel of attn.cu lost (MUFU 60 % busy) was the serial per-tile chain of its ONE softmax warp per 32 rows.
+//   * TWO softmax warpgroups per CTA on ALTERNATE key tiles (warpgroup 0 even j, warpgroup 1 odd j; warps w and w+4 reach the same
+//     TMEM lane quadrant): both S buffers are consumed at once and every scheduler holds four independent exp chains, one thread per
+//     row and tile as before.  The online softmax couples consecutive tiles only through the running max:
+//       m(j) from m(j-1)                            one float per row through shared memory + one mbarrier (m_full)
+//       O *= 2^(m(j-1) - m(j)) before PV(j)          done in-line by the thread that owns tile j (after step(j-1) retired)
+//       d                                            each warpgroup keeps the sum of ITS tiles relative to its last max; the two
+//                                                    partial sums are combined once in the epilogue
+//   * LAZY running max (SAB_ALT_TAU = 4 binades): the max moves only when an element of the tile would overflow e4m3 (P > 448);
+//     when it moves, the new row maximum is placed tau binades below 448 (exponent offset 8.807 - tau), so the in-line O rescale —
+//     128 TMEM columns read and written per row — runs in ~0.2 % of the warp-tiles instead of ~80 % with the reference's exact max.
+//     P keeps e4m3's relative precision (a floating format); only the tail below 2^-9 is cut 2^tau earlier.  P is therefore a
+//     different rounding realisation than the reference kernel's (same accuracy against exact attention, tests/test_gpu_parity.py);
+//     SAB_ATTN_KERNEL=exact selects the exact-max kernel of attn.cu.
+// 384 threads, registers 96 / 96 / 48 via setmaxnreg; no correction warpgroup.
+// Measured (B200, hd128 S=8192 non-causal, kernel only): 1307 TFLOP/s at tau = 0, 1438 at tau = 3, 1452 at tau = 4 (exact kernel: 1277).
 #include "attn_common.cuh"
 
 namespace sab {
 
 constexpr int kAltThreads = 384;   // warpgroups: 0 = softmax of even key tiles, 1 = softmax of odd key tiles, 2 = TMA / MMA / 2 idle
 #ifndef SAB_ALT_TAU
-#define SAB_ALT_TAU 0
+#define SAB_ALT_TAU 4   // lazy-max threshold in binades (0: the reference's exact running max; measured on B200: 1307 / 1438 / 1452 TFLOP/s at tau 0 / 3 / 4)
 #endif
 
 // 128 x (96 + 96 + 48) = 30720 = the CTA's register pool (80 x 384); multiples of 16 (see attn_split.cu)

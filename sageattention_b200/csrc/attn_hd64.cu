@@ -14,11 +14,12 @@ namespace sab {
 
 constexpr int kHd64Threads = 256;
 constexpr uint32_t kHd64TmemCols = 128;
+constexpr float kLazyTau = 4.0f;   // lazy-max threshold in binades (same rule as attn_alt.cu)
 
 __device__ __forceinline__ void setmaxnreg_inc_96() { asm volatile("setmaxnreg.inc.sync.aligned.u32 96;"); }
 __device__ __forceinline__ void setmaxnreg_dec_32() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); }
 
-template <bool kKT, typename OutT>
+template <bool kKT, typename OutT, bool kLazy>
 __global__ void __launch_bounds__(kHd64Threads, 4)
 sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -212,14 +213,16 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if constexpr (MASKED) c = (v == kIntSentinel) ? kMaskValue : c;
           mx = fmaxf(mx, c);
         }
-#ifdef SAB_LAZY_RESCALE
-        // opt-in build (see attn.cu): the max moves only when it grew by more than 2^tau, so the in-line O rescale below — about
-        // 70 of this issue-bound kernel's ~420 warp instructions per tile when it runs — happens in a few percent of the tiles
-        const float m_true = fmaxf(m, mx - (kFp8Offset - float(SAB_LAZY_RESCALE)));
-        const float m_new = (m_true - m > float(SAB_LAZY_RESCALE)) ? m_true : m;
-#else
-        const float m_new = fmaxf(m, mx - kFp8Offset);   // update_mdo, attn_utils.cuh:377-396
-#endif
+        // kLazy: the max moves only when a P of this tile would overflow e4m3 (it grew by more than 2^tau past the point where the
+        // current maximum was placed), so the in-line O rescale below — ~70 of this issue-bound kernel's ~420 warp instructions per
+        // tile when it runs — happens in well under 1 % of the tiles; else the reference's exact max (update_mdo, attn_utils.cuh:377-396)
+        float m_new;
+        if constexpr (kLazy) {
+          const float m_true = fmaxf(m, mx - (kFp8Offset - kLazyTau));
+          m_new = (m_true - m > kLazyTau) ? m_true : m;
+        } else {
+          m_new = fmaxf(m, mx - kFp8Offset);
+        }
         const float alpha = ex2_approx(m - m_new);
         d *= alpha;
         m = m_new;
@@ -241,17 +244,8 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const uint64_t f2 = pack_f2(__int2float_rn(int(s[i])), __int2float_rn(int(s[i + 1])));
             float y0, y1;
             unpack_f2(ffma2(f2, coef2[g], nm2), y0, y1);
-#ifdef SAB_POLY_EXP_PAIRS
-            if (((i >> 1) & 3) < SAB_POLY_EXP_PAIRS) {   // opt-in build: this pair on the FMA pipe (ptx.cuh ex2_poly2)
-              ex2_poly2(y0, y1, e[u], e[u + 1]);
-            } else {
-              e[u] = ex2_approx(y0);
-              e[u + 1] = ex2_approx(y1);
-            }
-#else
             e[u] = ex2_approx(y0);
             e[u + 1] = ex2_approx(y1);
-#endif
             if constexpr (MASKED) {
               e[u] = (i < limit) ? e[u] : 0.f;
               e[u + 1] = (i + 1 < limit) ? e[u + 1] : 0.f;
@@ -345,12 +339,12 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 5) tmem_dealloc<kHd64TmemCols>(tmem_base);
 }
 
-template <bool kKT, typename OutT>
+template <bool kKT, typename OutT, bool kLazy>
 int launch_attn_hd64(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                      cudaStream_t stream) {
   constexpr int NS = 5;
   const size_t smem = size_t(BM) * 64 + size_t(NS) * 2 * BN * 64 + 256;   // 49.3 KB -> four CTAs per SM
-  auto kern = sage_attn_hd64_kernel<kKT, OutT>;
+  auto kern = sage_attn_hd64_kernel<kKT, OutT, kLazy>;
   static bool configured[64] = {};
   if (int st = ensure_dynamic_smem(kern, smem, configured)) return st;
   kern<<<grid, kHd64Threads, smem, stream>>>(tq, tk, tv, p);
@@ -358,9 +352,16 @@ int launch_attn_hd64(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   return SAB_OK;
 }
 
-template int launch_attn_hd64<true, __nv_bfloat16>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const AttnParams&, dim3, cudaStream_t);
-template int launch_attn_hd64<true, __half>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const AttnParams&, dim3, cudaStream_t);
-template int launch_attn_hd64<false, __nv_bfloat16>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const AttnParams&, dim3, cudaStream_t);
-template int launch_attn_hd64<false, __half>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const AttnParams&, dim3, cudaStream_t);
+#define SAB_INST(KT, T, LZ) \
+  template int launch_attn_hd64<KT, T, LZ>(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const AttnParams&, dim3, cudaStream_t);
+SAB_INST(true, __nv_bfloat16, true)
+SAB_INST(true, __half, true)
+SAB_INST(false, __nv_bfloat16, true)
+SAB_INST(false, __half, true)
+SAB_INST(true, __nv_bfloat16, false)
+SAB_INST(true, __half, false)
+SAB_INST(false, __nv_bfloat16, false)
+SAB_INST(false, __half, false)
+#undef SAB_INST
 
 }  // namespace sab

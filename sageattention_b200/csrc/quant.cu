@@ -4,6 +4,7 @@
 // one read of the input (+ one statistics pre-pass where the algorithm needs a full-sequence reduction),
 // 64/128-bit stores.  Semantics follow csrc/fused/fused.cu and sageattention/triton/quant_per_*.py of the
 // reference (see include/sageattn_b200.h for the per-entry citations).
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -418,6 +419,7 @@ __global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p)
 // HBM sees K once instead of twice (stats pass + quant pass) and two launches disappear.
 // =====================================================================================================
 constexpr int kKCluster = 8;
+constexpr int kFusedDynSmem = 0;   // default dynamic shared-memory request of the fused kernels (see launch_cluster)
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -463,24 +465,6 @@ __device__ __forceinline__ void cluster_channel_sums(const T* base, int64_t ss, 
     for (int r = 0; r < RPP; ++r) a += s_red[r][threadIdx.x];
     s_part[threadIdx.x] = a;
   }
-}
-
-// The mean alone, with the summation order of the fused kernel below (so that `k_mean` + a quantiser == the fused call, bit for bit).
-template <typename T, int D>
-__global__ void __launch_bounds__(256) k_mean_cluster_kernel(const T* __restrict__ x, T* __restrict__ mean_out, int H, int S, int64_t sb,
-                                                             int64_t sh, int64_t ss) {
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int rank = int(cluster_ctarank());
-  __shared__ float s_part[D];
-  cluster_channel_sums<T, D>(x + int64_t(b) * sb + int64_t(h) * sh, ss, S, rank, s_part);
-  cluster_sync_all();
-  if (rank == 0 && threadIdx.x < D) {
-    float a = 0.f;
-#pragma unroll
-    for (int r = 0; r < kKCluster; ++r) a += ld_dsmem_f32(&s_part[threadIdx.x], uint32_t(r));
-    mean_out[(int64_t(b) * H + h) * D + threadIdx.x] = from_f<T>(__fdiv_rn(a, float(S)));
-  }
-  cluster_sync_all();
 }
 
 template <typename T, int D, int MODE, int FLAGS>
@@ -745,8 +729,16 @@ using namespace sab;
 // ---------------------------------------------------------------------------------------------- fused single-pass front-end
 template <typename Kern, typename... Args>
 static int launch_cluster(Kern kern, dim3 grid, cudaStream_t st, Args... args) {
+  // Occupancy knob: every resident cluster keeps one (b,h) slice in flight between its two phases and the second read should hit
+  // L2, so the number of co-resident clusters is bounded through a dynamic shared-memory request (unused by the kernels).
+  static int dyn = -1;
+  if (dyn < 0) {
+    const char* e = getenv("SAB_FUSED_DYNSMEM");
+    dyn = e ? atoi(e) : kFusedDynSmem;
+  }
+  if (dyn > 0) SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = size_t(dyn); cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kKCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -767,16 +759,16 @@ extern "C" int sab_k_mean(const void* k, int dtype, void* mean, int B, int H, in
                           int64_t stride_h, int64_t stride_s, void* workspace, void* stream) {
   int st = check_common(k, dtype, D, stride_b, stride_h, stride_s);
   if (st) return st;
-  SAB_REQUIRE(mean && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_k_mean");
-  (void)workspace;   // kept in the signature (and sized by sab_k_mean_workspace_bytes) for ABI stability; the cluster kernel needs none
+  SAB_REQUIRE(mean && workspace && B > 0 && H > 0 && S > 0, SAB_ERR_INVALID, "bad arguments to sab_k_mean");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const dim3 grid(kKCluster, H, B);
-  if (dtype == SAB_DTYPE_FP16) {
-    if (D == 128) return launch_cluster(k_mean_cluster_kernel<__half, 128>, grid, s, reinterpret_cast<const __half*>(k), reinterpret_cast<__half*>(mean), H, S, stride_b, stride_h, stride_s);
-    return launch_cluster(k_mean_cluster_kernel<__half, 64>, grid, s, reinterpret_cast<const __half*>(k), reinterpret_cast<__half*>(mean), H, S, stride_b, stride_h, stride_s);
-  }
-  if (D == 128) return launch_cluster(k_mean_cluster_kernel<__nv_bfloat16, 128>, grid, s, reinterpret_cast<const __nv_bfloat16*>(k), reinterpret_cast<__nv_bfloat16*>(mean), H, S, stride_b, stride_h, stride_s);
-  return launch_cluster(k_mean_cluster_kernel<__nv_bfloat16, 64>, grid, s, reinterpret_cast<const __nv_bfloat16*>(k), reinterpret_cast<__nv_bfloat16*>(mean), H, S, stride_b, stride_h, stride_s);
+  if ((st = run_stats(k, dtype, reinterpret_cast<float*>(workspace), B, H, S, D, stride_b, stride_h, stride_s, s))) return st;
+  const int nchunk = (S + kStatChunk - 1) / kStatChunk;
+  if (dtype == SAB_DTYPE_FP16)
+    channel_stats_stage2<__half><<<B * H, 128, 0, s>>>(reinterpret_cast<float*>(workspace), nchunk, D, S, 0, reinterpret_cast<__half*>(mean), nullptr, nullptr, 0.f, nullptr);
+  else
+    channel_stats_stage2<__nv_bfloat16><<<B * H, 128, 0, s>>>(reinterpret_cast<float*>(workspace), nchunk, D, S, 0, reinterpret_cast<__nv_bfloat16*>(mean), nullptr, nullptr, 0.f, nullptr);
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
 }
 
 extern "C" int sab_quant_per_block_int8(const void* x, int dtype, const void* mean, int8_t* out, float* scale, int B,

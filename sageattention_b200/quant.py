@@ -103,7 +103,10 @@ def quant_k_int8(k: torch.Tensor, km: Optional[torch.Tensor] = None, qk_quant_gr
 def smooth_quant_k(k: torch.Tensor, qk_quant_gran: str = "per_thread", tensor_layout: str = "HND"):
     """`km = k.mean(dim=seq, keepdim=True)` (sageattention/core.py:773) + the K half of per_thread_int8 / per_warp_int8 in ONE launch
     (csrc/quant.cu k_smooth_quant_kernel: a thread-block cluster per (b,h) reduces the mean through distributed shared memory and
-    quantises right away, so K crosses HBM once).  Returns (km, k_int8, k_scale), bit-identical to k_mean() + quant_k_int8()."""
+    quantises right away, so K crosses HBM once).  Returns (km, k_int8, k_scale); k_int8 / k_scale are bit-identical to
+    quant_k_int8(k, km) with the returned km (km itself is a different fp32 summation order than k_mean(): same value up to one
+    ulp on rare channels).  OPT-IN: measured on B200 the one launch is slower than k_mean + quant_k_int8 (177 vs 153 us at
+    4x32x8192x128) — the quantisers are latency- not bandwidth-bound, so saving the second HBM read does not pay."""
     from ._capi import SAB_GRAN_PER_WARP, SAB_GRAN_PER_THREAD
     b, h_kv, kv_len, head_dim = _dims(k, tensor_layout)
     lay = _layout(tensor_layout)
@@ -166,7 +169,7 @@ def per_block_int8_varlen(q, k, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_se
     return q_int8, q_scale, k_int8, k_scale, cu_seqlens_q_scale, cu_seqlens_k_scale
 
 
-def per_channel_fp8(v: torch.Tensor, tensor_layout: str = "HND", scale_max: float = 448.0, smooth_v: bool = True):
+def per_channel_fp8(v: torch.Tensor, tensor_layout: str = "HND", scale_max: float = 448.0, smooth_v: bool = True, fused: bool = False):
     """Per-channel e4m3 quantisation of V (sageattention/quant.py:224-293).
     Returns (v_fp8, v_scale, vm).  v_fp8 is ``[B, H_kv, D, ceil(kv_len/128)*128]`` float8_e4m3fn
     (token-contiguous "V transposed", zero padded) for BOTH layouts; unlike the reference it is not
@@ -176,7 +179,10 @@ def per_channel_fp8(v: torch.Tensor, tensor_layout: str = "HND", scale_max: floa
     v_fp8 = torch.empty((b, h_kv, head_dim, padded_len), dtype=torch.float8_e4m3fn, device=v.device)
     v_scale = torch.empty((b, h_kv, head_dim), dtype=torch.float32, device=v.device)
     vm = torch.empty((b, h_kv, head_dim), dtype=torch.float32, device=v.device) if smooth_v else None
-    ops.per_channel_fp8_fused(v, v_fp8, v_scale, vm, _layout(tensor_layout), scale_max)   # statistics + quantisation in one launch
+    if fused:   # statistics + quantisation in one cluster launch (measured slower on B200, see DESIGN.md 4.2: opt-in)
+        ops.per_channel_fp8_fused(v, v_fp8, v_scale, vm, _layout(tensor_layout), scale_max)
+    else:
+        ops.per_channel_fp8(v, v_fp8, v_scale, vm, _layout(tensor_layout), scale_max)
     return v_fp8, v_scale, vm
 
 

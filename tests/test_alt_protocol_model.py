@@ -159,3 +159,4 @@ def test_bare_parity_waits_are_caught():
             except (AssertionError, KeyError):
                 bad += 1
     assert bad > 0
+

@@ -1,6 +1,9 @@
 #!/bin/bash
 export PYTHONUNBUFFERED=1
-L=$PWD/sageattention_b200/lib
 mkdir -p gpurun_out
-for v in t2_base t2_p8 t2_a_p8 t2_a_p6 t2_ad_p12 t2_d_p8; do SAB_LIB_PATH=$L/libsab_$v.so timeout 200 python tools/perf_kernel.py short2 > gpurun_out/perf_$v.log 2>&1; echo "$v: $(tail -1 gpurun_out/perf_$v.log | cut -d' ' -f2-)"; done
-SAB_ATTN_KERNEL=alt SAB_LIB_PATH=$L/libsab_alt_tau4.so timeout 200 python tools/perf_kernel.py short2 > gpurun_out/perf_alt_tau4.log 2>&1; echo "alt_tau4: $(tail -1 gpurun_out/perf_alt_tau4.log | cut -d' ' -f2-)"
+timeout 300 python tools/first_run_check.py > gpurun_out/first_run_check.log 2>&1; tail -2 gpurun_out/first_run_check.log
+timeout 1800 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1; tail -8 gpurun_out/gpu_tests.log
+timeout 300 python tools/perf_kernel.py > gpurun_out/perf_product.log 2>&1; tail -1 gpurun_out/perf_product.log
+timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 600 gpurun_out/bench_n1.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>&1; tail -c 400 gpurun_out/bench_ref.json
+timeout 1200 python tools/profile_round.py capture r02 > gpurun_out/profile_capture.log 2>&1; tail -5 gpurun_out/profile_capture.log

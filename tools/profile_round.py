@@ -16,7 +16,8 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
            "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second",
-           "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum"]
+           "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+           "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]
 
 
 def capture(tag):
@@ -25,7 +26,7 @@ def capture(tag):
     cmds = [
         # launch list of one bench invocation: kernel SHARES of the step (cold-cache, serialised)
         ["ncu", "--metrics", "gpu__time_duration.sum", "--clock-control", "none", "-c", "400", "--csv", "--log-file",
-         os.path.join(OUT, f"{tag}_launches.csv"), py, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline"],
+         os.path.join(OUT, f"{tag}_launches.csv"), py, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-sweep"],
         # full capture of the dominant kernel at the headline shape (third launch), source pages included (-lineinfo build)
         ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", "regex:sage_attn", "-s", "2", "-c", "1", "-f",
          "-o", os.path.join(OUT, f"{tag}_attn"), py, os.path.join(ROOT, "tools", "run_attn_once.py"), "4", "32", "8192", "128", "0", "per_thread", "3"],
