@@ -582,10 +582,10 @@ static bool exact_max_mode() {
 template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false, bool kSeg = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
-  if constexpr (D == 128 && !kPV16 && !kSeg) {
+  if constexpr (D == 128 && !kPV16) {   // also the fused-gather form: the producers poll p.seg_flags at run time
     if (!exact_max_mode() && p.dbg == nullptr) return launch_attn_alt<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
   }
-  if constexpr (D == 64 && !kPV16 && !kSeg) {
+  if constexpr (D == 64 && !kPV16) {
     if (use_hd64_kernel() && p.dbg == nullptr) {
       if (exact_max_mode()) return launch_attn_hd64<kKT, OutT, false>(tq, tk, tv, p, grid, stream);
       return launch_attn_hd64<kKT, OutT, true>(tq, tk, tv, p, grid, stream);
@@ -689,6 +689,13 @@ static int attn_entry(int pv16, const int8_t* q_int8, const int8_t* k_int8, cons
   p.cu_q = cu_seqlens_q; p.cu_k = cu_seqlens_k; p.cu_v = cu_pad_v; p.cu_qs = cu_q_scale; p.cu_ks = cu_k_scale;
   p.causal_q_offset = causal_q_offset; p.kv_seg_len = kv_seg_len;
   p.dbg = debug_dump;
+  if (!varlen && !pv16 && Sq > 0) {   // consumed by attn_alt.cu (D = 128: two 128-byte halves) and attn_hd64.cu
+    // rows past Sq are clipped by the map, so the epilogue can store whole 128-row tiles
+    if ((st = make_map_u8(&p.o_map, out, uint64_t(D) * 2, Sq, Hq, B, uint64_t(o_stride_s) * 2, uint64_t(o_stride_h) * 2,
+                          uint64_t(o_stride_b) * 2, 128, BM, 128)))
+      return st;
+    p.o_tma = 1;
+  }
 
   dim3 grid(p.n_q_tiles, Hq, B);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -38,7 +38,7 @@ __device__ __forceinline__ void alt_bar_sync() { asm volatile("bar.sync 1, 256;"
 template <int D, bool kKT, typename OutT>
 __global__ void __launch_bounds__(kAltThreads, 2)
 sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   constexpr uint32_t K_TILE = BN * D;
   constexpr uint32_t V_TILE = D * BN;
   constexpr int NS = (D == 128) ? 5 : 10;
@@ -117,6 +117,7 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (lane == 0 && n_kv > 0) {
         mbar_expect_tx(q_full, Q_BYTES);
         tma_load_4d(sQ, &tmQ, q_full, 0, q_off + qt * BM, h, tb);
+        int ready_seg = -1;
         for (int j = 0; j < n_kv; ++j) {
           const int s = j % NS;
           const uint32_t ph = (j / NS) & 1;
@@ -125,6 +126,17 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int seg = (j * BN) / p.kv_seg_len;
             kc = vc = j * BN - seg * p.kv_seg_len;
             kb = seg * p.B + b;
+            if (p.seg_flags != nullptr && seg != ready_seg) {
+              // gather fused into the launch: first tile of a segment -> has the peer copy of this (head group, segment) landed?
+              const uint32_t* flag = p.seg_flags + (hk / p.seg_heads) * (p.Sk / p.kv_seg_len) + seg;
+              const long long t0 = clock64();
+              while (ld_acquire_sys_u32(flag) != p.seg_epoch) {
+                __nanosleep(200);
+                if (clock64() - t0 > (8ll << 30)) __trap();   // ~4 s: the copies never came; fail the launch instead of hanging
+              }
+              fence_proxy_async_all();
+              ready_seg = seg;
+            }
           }
           mbar_wait_wd(kv_empty + s, ph ^ 1);
           mbar_expect_tx(kv_full + s, K_TILE + V_TILE);
@@ -372,9 +384,17 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     d = d * ex2_approx(m_own - m_fin) + d_o * ex2_approx(m_o - m_fin);
 
     const uint32_t tOh = tO + wg * OC;
-    OutT* orow = reinterpret_cast<OutT*>(p.out) + (varlen ? 0 : int64_t(b) * p.o_stride_b) + int64_t(h) * p.o_stride_h +
-                 int64_t(q_off + q_row) * p.o_stride_s + wg * OC;
     const bool row_ok = q_row < q_len;
+    auto out_row = [&]() {   // packed varlen rows only
+      return reinterpret_cast<OutT*>(p.out) + int64_t(h) * p.o_stride_h + int64_t(q_off + q_row) * p.o_stride_s + wg * OC;
+    };
+    // Dense outputs leave through TMA: each warpgroup stages its [128 rows][128 B] half of the tile in the (now idle) K ring
+    // with the 128-byte swizzle (conflict-free 16-byte shared stores) and one thread issues a bulk tensor store, which writes
+    // full lines and clips the rows past Sq.  Packed varlen outputs (per-sequence clipping) keep the direct row stores.
+    const bool use_tma = kTmaStoreEpilogue && p.o_tma != 0;
+    static_assert(OC * sizeof(OutT) == 128 && NS * K_TILE >= 2 * BM * 128, "staging tile is 128 rows x 128 bytes per warpgroup");
+    uint8_t* stage = sK + wg * (BM * 128);
+    const uint32_t stage_row = smem_u32(stage) + row * 128;
     const float* vs = p.v_scale ? p.v_scale + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D + wg * OC : nullptr;
     const float* vm = p.v_mean ? p.v_mean + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D + wg * OC : nullptr;
     if (n_kv > 0) {
@@ -398,16 +418,33 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
           o16[i / 2] = pack2<OutT>(a, c);
         }
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+        if (use_tma) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4)
+            st_shared_v4(stage_row + (((ch * 4 + v4) ^ (row & 7)) << 4), o16[4 * v4], o16[4 * v4 + 1], o16[4 * v4 + 2], o16[4 * v4 + 3]);
+        } else if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(out_row() + ch * 32);
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4) dst[v4] = make_uint4(o16[4 * v4], o16[4 * v4 + 1], o16[4 * v4 + 2], o16[4 * v4 + 3]);
         }
       }
+    } else if (use_tma) {
+#pragma unroll
+      for (int v4 = 0; v4 < OC / 8; ++v4) st_shared_v4(stage_row + (v4 << 4), 0u, 0u, 0u, 0u);
     } else if (row_ok) {
-      uint4* dst = reinterpret_cast<uint4*>(orow);
+      uint4* dst = reinterpret_cast<uint4*>(out_row());
 #pragma unroll
       for (int v4 = 0; v4 < OC / 8; ++v4) dst[v4] = make_uint4(0, 0, 0, 0);
+    }
+    if (use_tma) {
+      fence_proxy_async_smem();                                        // generic-proxy stores -> visible to the TMA engine
+      if (wg == 0) asm volatile("bar.sync 2, 128;" ::: "memory");      // this warpgroup's half tile is staged
+      else asm volatile("bar.sync 3, 128;" ::: "memory");
+      if ((threadIdx.x & 127) == 0) {
+        tma_store_4d(&p.o_map, stage, wg * 128, q_row - row, blockIdx.y, blockIdx.z);
+        tma_store_commit();
+        tma_store_wait_read();                                         // the staging buffer must outlive the read
+      }
     }
     if (p.lse != nullptr && row_ok && wg == 0) {
       const int64_t li = varlen ? (int64_t(h) * p.Sq + q_off + q_row) : ((int64_t(b) * p.Hq + h) * p.Sq + q_row);

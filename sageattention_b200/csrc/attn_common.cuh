@@ -1,6 +1,7 @@
-// Shared declarations of the attention kernels (attn.cu: one Q tile per CTA, two CTAs per SM; attn_pair.cu: two Q tiles
-// per CTA with explicit exp ping-pong).
+// Shared declarations of the attention kernels (attn_alt.cu: head_dim 128 product kernel; attn_hd64.cu: head_dim 64;
+// attn.cu: exact-max / fp16-PV / masked / sequence-parallel variants and the host dispatch).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <type_traits>
@@ -22,6 +23,11 @@ constexpr uint32_t kTmemCols = 256;
 constexpr float kFp8Offset = 8.807f;      // attn_utils.cuh:30
 constexpr float kMaskValue = -5000000.0f; // attn_utils.cuh:310
 constexpr int kIntSentinel = -(1 << 30);
+#ifdef SAB_NO_TMA_STORE   // A/B switch: direct per-row global stores in the epilogue
+constexpr bool kTmaStoreEpilogue = false;
+#else
+constexpr bool kTmaStoreEpilogue = true;
+#endif
 constexpr int kAlphaCol = 40;  // column of an S buffer (beyond the 16 / 32 P columns) that carries alpha(j) to the correction warps
 
 struct AttnParams {
@@ -60,6 +66,9 @@ struct AttnParams {
   const uint32_t* seg_flags;   // nullable
   uint32_t seg_epoch;
   int seg_heads;               // KV heads per flag group
+  // dense outputs: byte-typed 4-D map of O (box 128 B x 128 rows, 128-byte swizzle) for the TMA-store epilogue of attn_alt.cu
+  int o_tma;                   // 1: o_map is valid
+  CUtensorMap o_map;
 };
 
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {

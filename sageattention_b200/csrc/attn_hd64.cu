@@ -22,7 +22,7 @@ __device__ __forceinline__ void setmaxnreg_dec_32() { asm volatile("setmaxnreg.d
 template <bool kKT, typename OutT, bool kLazy>
 __global__ void __launch_bounds__(kHd64Threads, 4)
 sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   constexpr int D = 64;
   constexpr int NS = 5;                          // K / V^T ring slots (64-key tiles)
   constexpr uint32_t Q_BYTES = BM * D, K_TILE = BN * D, V_TILE = D * BN;
@@ -92,6 +92,7 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (lane == 0 && n_kv > 0) {
         mbar_expect_tx(q_full, Q_BYTES);
         tma_load_4d(sQ, &tmQ, q_full, 0, q_off + qt * BM, h, tb);
+        int ready_seg = -1;
         for (int j = 0; j < n_kv; ++j) {
           const int s = j % NS;
           const uint32_t ph = (j / NS) & 1;
@@ -100,6 +101,17 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const int seg = (j * BN) / p.kv_seg_len;
             kc = vc = j * BN - seg * p.kv_seg_len;
             kb = seg * p.B + b;
+            if (p.seg_flags != nullptr && seg != ready_seg) {
+              // gather fused into the launch: first tile of a segment -> has the peer copy of this (head group, segment) landed?
+              const uint32_t* flag = p.seg_flags + (hk / p.seg_heads) * (p.Sk / p.kv_seg_len) + seg;
+              const long long t0 = clock64();
+              while (ld_acquire_sys_u32(flag) != p.seg_epoch) {
+                __nanosleep(200);
+                if (clock64() - t0 > (8ll << 30)) __trap();   // ~4 s: the copies never came; fail the launch instead of hanging
+              }
+              fence_proxy_async_all();
+              ready_seg = seg;
+            }
           }
           mbar_wait_wd(kv_empty + s, ph ^ 1);
           mbar_expect_tx(kv_full + s, K_TILE + V_TILE);
@@ -288,10 +300,15 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_arrive(p_full);
     }
 
-    // ---- epilogue
-    OutT* orow = reinterpret_cast<OutT*>(p.out) + (varlen ? 0 : int64_t(b) * p.o_stride_b) + int64_t(h) * p.o_stride_h +
-                 int64_t(q_off + q_row) * p.o_stride_s;
+    // ---- epilogue: dense outputs are staged in the idle K ring ([128 rows][128 B], 128-byte swizzle) and leave through one
+    // TMA store per CTA (full lines, rows past Sq clipped by the map); packed varlen rows are stored directly
     const bool row_ok = q_row < q_len;
+    auto out_row = [&]() {
+      return reinterpret_cast<OutT*>(p.out) + int64_t(h) * p.o_stride_h + int64_t(q_off + q_row) * p.o_stride_s;
+    };
+    const bool use_tma = kTmaStoreEpilogue && p.o_tma != 0;
+    static_assert(D * sizeof(OutT) == 128 && NS * K_TILE >= BM * 128, "staging tile is 128 rows x 128 bytes");
+    const uint32_t stage_row = smem_u32(sK) + row * 128;
     const float* vs = p.v_scale ? p.v_scale + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D : nullptr;
     const float* vm = p.v_mean ? p.v_mean + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D : nullptr;
     if (n_kv > 0) {
@@ -317,16 +334,32 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           }
           o16[i / 2] = pack2<OutT>(a, c);
         }
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+        if (use_tma) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4)
+            st_shared_v4(stage_row + (((ch * 4 + v4) ^ (row & 7)) << 4), o16[4 * v4], o16[4 * v4 + 1], o16[4 * v4 + 2], o16[4 * v4 + 3]);
+        } else if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(out_row() + ch * 32);
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4) dst[v4] = make_uint4(o16[4 * v4], o16[4 * v4 + 1], o16[4 * v4 + 2], o16[4 * v4 + 3]);
         }
       }
+    } else if (use_tma) {
+#pragma unroll
+      for (int v4 = 0; v4 < D / 8; ++v4) st_shared_v4(stage_row + (v4 << 4), 0u, 0u, 0u, 0u);
     } else if (row_ok) {
-      uint4* dst = reinterpret_cast<uint4*>(orow);
+      uint4* dst = reinterpret_cast<uint4*>(out_row());
 #pragma unroll
       for (int v4 = 0; v4 < D / 8; ++v4) dst[v4] = make_uint4(0, 0, 0, 0);
+    }
+    if (use_tma) {
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        tma_store_4d(&p.o_map, sK, 0, q_row - row, blockIdx.y, blockIdx.z);
+        tma_store_commit();
+        tma_store_wait_read();
+      }
     }
     if (p.lse != nullptr && row_ok) {
       const int64_t li = varlen ? (int64_t(h) * p.Sq + q_off + q_row) : ((int64_t(b) * p.Hq + h) * p.Sq + q_row);

@@ -246,12 +246,12 @@ def qk_int8_sv_f8_attn_sp(query: torch.Tensor, key: torch.Tensor, value: torch.T
                           k_quant_gran: int, sm_scale: float, kv_seg_len: int, seg_flags: torch.Tensor, seg_epoch: int,
                           heads_per_flag: int) -> None:
     """Sequence-parallel attention whose K/V segments may still be arriving (include/sageattn_b200.h, sab_qk_int8_sv_f8_attn_sp):
-    HND tensors, key [P*B,Hkv,kv_seg_len,D] / value [P*B,Hkv,D,kv_seg_len] rank-major, seg_flags int32 [Hkv/heads_per_flag * P];
+    HND tensors, key [P*B,Hkv,kv_seg_len,D] / value [P*B,Hkv,D,kv_seg_len] rank-major, seg_flags uint32 [Hkv/heads_per_flag * P];
     the kernel waits for seg_flags[group * P + segment] == seg_epoch before the first tile of a segment.  Non-causal."""
     B, Hq, Sq, D = query.shape
     Hkv = key.size(1)
     P = key.size(0) // B
-    assert seg_flags.dtype == torch.int32 and seg_flags.is_contiguous() and seg_flags.numel() >= (Hkv // heads_per_flag) * P
+    assert seg_flags.dtype in (torch.int32, torch.uint32) and seg_flags.is_contiguous() and seg_flags.numel() >= (Hkv // heads_per_flag) * P
     qs, ks, os_ = _bhs_strides(query, 1), _bhs_strides(key, 1), _bhs_strides(output, 1)
     with torch.cuda.device(query.device):
         check(lib().sab_qk_int8_sv_f8_attn_sp(query.data_ptr(), key.data_ptr(), value.data_ptr(), output.data_ptr(), None,

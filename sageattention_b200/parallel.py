@@ -97,7 +97,7 @@ class _FusedGatherWorkspace:
         self.v_all = self.buf[world * self.nk:].view(torch.float8_e4m3fn).view(self.shape_v)
         self.k_local = self.k_all[rank * B:(rank + 1) * B]
         self.v_local = self.v_all[rank * B:(rank + 1) * B]
-        self.flags = torch.zeros((n_chunks * world,), dtype=torch.int32, device=dev)
+        self.flags = torch.zeros((n_chunks * world,), dtype=torch.uint32, device=dev)   # stream_write_value32 wants a flat uint32 tensor
         self.epoch = 0
 
     def peer_shard(self, src):

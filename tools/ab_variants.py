@@ -16,33 +16,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    # name: (defines, what it changes)
-    "poly1": (["SAB_POLY_EXP_PAIRS=1"], "25 % of the exponentials as a degree-3 polynomial on the FMA pipe (ptx.cuh ex2_poly2)"),
-    "poly2": (["SAB_POLY_EXP_PAIRS=2"], "50 % of the exponentials on the FMA pipe"),
-    "premax8": (["SAB_PREMAX=8"], "row maxima of S(j+1) gathered inside the exp loop of tile j (8-column chunks)"),
-    "defer": (["SAB_DEFER_PST"], "hand-off of P(j-1) (wait::st + fence + arrive) taken after S(j) was loaded, off the serial chain"),
-    "late_alpha": (["SAB_LATE_ALPHA"], "alpha published after the first 8 exponentials of the tile instead of before the loop"),
-    "all_chain": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_LATE_ALPHA"], "the three chain shorteners together (P stays bit-identical)"),
-    "lazy3": (["SAB_LAZY_RESCALE=3"], "running max moves only when it grew by > 2^3: O rescale in ~3 % of the warp-tiles instead of ~80 %"),
-    "all_chain_lazy3": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_LATE_ALPHA", "SAB_LAZY_RESCALE=3"], "chain shorteners + lazy rescale"),
-    "lazy3_poly1": (["SAB_LAZY_RESCALE=3", "SAB_POLY_EXP_PAIRS=1"], "lazy rescale + 25 % polynomial exp2 (the hd64 kernel is issue-bound: fewer rescale instructions make room for the polynomial)"),
-    "defer_premax8": (["SAB_DEFER_PST", "SAB_PREMAX=8"], "both chain shorteners"),
-    "defer_premax8_poly1": (["SAB_DEFER_PST", "SAB_PREMAX=8", "SAB_POLY_EXP_PAIRS=1"], "chain shorteners + 25 % polynomial exp2"),
+    # name: (defines, what it changes).  The round-2 experiments whose macros were deleted with the losing code paths
+    # (polynomial exp2, premax, deferred hand-off, pair / split / speculative kernels) are recorded in profiles/r02_ab_*.log.
+    "wd": (["SAB_WATCHDOG"], "bounded mbarrier waits (attn_common.cuh mbar_wait_wd): run FIRST after touching a barrier protocol"),
+    "tau3": (["SAB_ALT_TAU=3"], "attn_alt.cu lazy running max with tau = 3 binades (more rescales, smaller P range)"),
+    "tau5": (["SAB_ALT_TAU=5"], "attn_alt.cu lazy running max with tau = 5 binades"),
+    "nostore": (["SAB_NO_TMA_STORE"], "direct per-row global stores in the epilogue instead of the staged TMA store"),
 }
-# attn_alt.cu (two softmax warpgroups on alternate key tiles) is selected at run time, on any library
-ENVS = {
-    "alt_wd": {"SAB_ATTN_KERNEL": "alt"},
-    "alt": {"SAB_ATTN_KERNEL": "alt"},
-    "alt_tau3": {"SAB_ATTN_KERNEL": "alt"},
-    "alt_tau3_poly1": {"SAB_ATTN_KERNEL": "alt"},
-}
-VARIANTS.update({
-    # watchdog build first: a wait that never completes reports itself (block 0) and is abandoned instead of hanging the GPU
-    "alt_wd": (["SAB_WATCHDOG"], "attn_alt.cu with bounded mbarrier waits (attn_common.cuh mbar_wait_wd): run BEFORE the other alt variants"),
-    "alt": ([], "attn_alt.cu with the exact max rule (in-line O rescale in most tiles)"),
-    "alt_tau3": (["SAB_ALT_TAU=3"], "attn_alt.cu with the lazy max (tau = 3)"),
-    "alt_tau3_poly1": (["SAB_ALT_TAU=3", "SAB_POLY_EXP_PAIRS=1"], "attn_alt.cu, lazy max, 25 % polynomial exp2"),
-})
+ENVS = {}   # per-variant environment (e.g. {"exact": {"SAB_ATTN_KERNEL": "exact"}} selects the exact-max kernels of any build)
+ENVS["exact"] = {"SAB_ATTN_KERNEL": "exact"}
+VARIANTS["exact"] = ([], "the exact-max kernels (attn.cu / attn_hd64.cu kLazy=false) of the product build")
 PARITY_K = "attention_vs_oracle or full_size_config1 or api_behaviour"
 
 
@@ -52,8 +35,8 @@ def build(names=()):
         if names and name not in names:
             continue
         t0 = time.time()
-        if not defs:      # run-time variant of the product library: build it as a variant all the same (one path in run())
-            defs = ["SAB_VARIANT_TAG=1"]
+        if not defs:      # run-time variant of the product library: nothing to build
+            continue
         lib = b.build(variant=name, defines=defs)
         print(f"[build] {name:16s} {time.time() - t0:5.1f} s  {lib}  ({what})", flush=True)
 
@@ -70,12 +53,12 @@ def run(names, top_k=3):
     """Kernel timing for every variant first (cheap), then the parity subset only for the product and the top_k fastest
     variants (by the first shape: hd128 S=8192 non-causal per-thread)."""
     libdir = os.path.join(ROOT, "sageattention_b200", "lib")
-    todo = [("product", None)] + [(n, os.path.join(libdir, f"libsab_{n}.so")) for n in (names or VARIANTS)]
+    todo = [("product", None)] + [(n, os.path.join(libdir, f"libsab_{n}.so") if VARIANTS[n][0] else None) for n in (names or VARIANTS)]
     alt_ok = True
     score, envs = {}, {}
     for name, lib in todo:
-        if name.startswith("alt") and name != "alt_wd" and not alt_ok:
-            print(f"== {name}: skipped (alt_wd did not pass)", flush=True)
+        if name != "wd" and not alt_ok:
+            print(f"== {name}: skipped (the watchdog build did not pass)", flush=True)
             continue
         if lib is not None and not os.path.exists(lib):
             print(f"== {name}: {lib} not built (python tools/ab_variants.py build)", flush=True)
@@ -88,18 +71,18 @@ def run(names, top_k=3):
         rc, out, err = _sub([sys.executable, os.path.join(ROOT, "tools", "perf_kernel.py")], env, 150)
         if rc is None:
             print(f"== {name}: perf TIMEOUT (variant hangs?)", flush=True)
-            if name == "alt_wd":
+            if name == "wd":
                 alt_ok = False
             continue
         tail = (out.strip().splitlines() or [""])[-1]
         print(f"== {name}: perf rc={rc}: {tail}", flush=True)
-        if name == "alt_wd" and (rc != 0 or "mbarrier timeout" in out + err):
+        if name == "wd" and (rc != 0 or "mbarrier timeout" in out + err):
             alt_ok = False
         if rc != 0:
             print("   " + "\n   ".join((out + err).strip().splitlines()[-12:]), flush=True)
             continue
         m = re.search(r"per_thread: (\d+)", tail)
-        if m and name != "alt_wd":
+        if m and name != "wd":
             score[name] = int(m.group(1))
     best = sorted((n for n in score if n != "product"), key=lambda n: -score[n])[:top_k]
     for name in ["product"] + best:
