@@ -686,6 +686,7 @@ static int attn_entry(int pv16, const int8_t* q_int8, const int8_t* k_int8, cons
   p.ks_stride_bh = int64_t((Skv + 63) / 64) * p.k_mult;
   p.qs_stride_idx = varlen ? Hq : 1;
   p.ks_stride_idx = varlen ? Hkv : 1;
+  p.ks_vec4 = (k_gran == SAB_GRAN_PER_THREAD && !varlen && aligned16(k_scale)) ? 1 : 0;
   p.cu_q = cu_seqlens_q; p.cu_k = cu_seqlens_k; p.cu_v = cu_pad_v; p.cu_qs = cu_q_scale; p.cu_ks = cu_k_scale;
   p.causal_q_offset = causal_q_offset; p.kv_seg_len = kv_seg_len;
   p.dbg = debug_dump;

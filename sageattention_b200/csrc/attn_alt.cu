@@ -227,8 +227,17 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int j = wg; j < n_kv; j += 2) {
       const uint32_t tS = tmem_base + lane_off + (j & 1) * BN;
       float coef[NG];
+      if constexpr (kKT) {
+        if (p.ks_vec4) {   // dense: the four per-thread scales of a key tile are one aligned 16-byte word
+          const float4 k4 = *reinterpret_cast<const float4*>(ks_base + int64_t(k_blk0 + j) * 4);
+          coef[0] = k4.x * qss; coef[1] = k4.y * qss; coef[2] = k4.z * qss; coef[NG - 1] = k4.w * qss;
+        } else {
 #pragma unroll
-      for (int g = 0; g < NG; ++g) coef[g] = ks_base[int64_t((k_blk0 + j) * NG + g) * p.ks_stride_idx] * qss;
+          for (int g = 0; g < NG; ++g) coef[g] = ks_base[int64_t((k_blk0 + j) * NG + g) * p.ks_stride_idx] * qss;
+        }
+      } else {
+        coef[0] = ks_base[int64_t(k_blk0 + j) * p.ks_stride_idx] * qss;
+      }
       int limit = kv_len - j * BN;
       if (p.causal) limit = min(limit, p.causal_q_offset + q_row - j * BN + 1);
       const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && (j + 1) * BN > p.causal_q_offset + qt * BM + 1);
@@ -282,8 +291,11 @@ sage_attn_alt_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #endif
         s_m[(j & 1) * BM + row] = m_new;
         mbar_arrive(m_full + (j & 1));
-        const float alpha_o = ex2_approx(m_prev - m_new);     // rescale of O before PV(j): consecutive tiles
-        d *= ex2_approx(m_own - m_new);                        // my partial sum: relative to my previous tile (j-2)
+        float alpha_o = 1.0f;                                   // rescale of O before PV(j): consecutive tiles
+        if (__any_sync(0xffffffffu, (m_new != m_prev) | (m_new != m_own))) {   // lazy max: rare after the first tiles (ex2(0) = 1)
+          alpha_o = ex2_approx(m_prev - m_new);
+          d *= ex2_approx(m_own - m_new);                        // my partial sum: relative to my previous tile (j-2)
+        }
         m_own = m_new;
 
         uint64_t coef2[NG];

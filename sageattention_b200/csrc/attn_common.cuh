@@ -49,6 +49,7 @@ struct AttnParams {
   int64_t ks_stride_bh;
   int qs_stride_idx;     // dense 1, varlen Hq
   int ks_stride_idx;     // dense 1, varlen Hkv
+  int ks_vec4;           // per-thread K scales, dense, 16-byte aligned: the four scales of a key tile load as one float4
   const int32_t* cu_q;   // varlen (nullable)
   const int32_t* cu_k;
   const int32_t* cu_v;

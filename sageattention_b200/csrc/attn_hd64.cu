@@ -179,7 +179,14 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int j = 0; j < n_kv; ++j) {
       float coef[NG];
 #pragma unroll
-      for (int g = 0; g < NG; ++g) coef[g] = ks_base[int64_t((k_blk0 + j) * NG + g) * p.ks_stride_idx] * qss;
+      for (int g = 0; g < NG; ++g) coef[g] = 0.f;
+      if (kKT && p.ks_vec4) {   // dense per-thread scales: the four scales of a key tile are one aligned 16-byte word
+        const float4 k4 = *reinterpret_cast<const float4*>(ks_base + int64_t(k_blk0 + j) * 4);
+        coef[0] = k4.x * qss; coef[NG > 1 ? 1 : 0] = k4.y * qss; coef[NG > 2 ? 2 : 0] = k4.z * qss; coef[NG - 1] = k4.w * qss;
+      } else {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) coef[g] = ks_base[int64_t((k_blk0 + j) * NG + g) * p.ks_stride_idx] * qss;
+      }
       int limit = kv_len - j * BN;
       if (p.causal) limit = min(limit, p.causal_q_offset + q_row - j * BN + 1);
       const bool masked_tile = (kv_len - j * BN < BN) || (p.causal && (j + 1) * BN > p.causal_q_offset + qt * BM + 1);
@@ -235,8 +242,11 @@ sage_attn_hd64_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         } else {
           m_new = fmaxf(m, mx - kFp8Offset);
         }
-        const float alpha = ex2_approx(m - m_new);
-        d *= alpha;
+        float alpha = 1.0f;
+        if (!kLazy || __any_sync(0xffffffffu, m_new != m)) {   // lazy max: rare after the first tiles (ex2(0) = 1 exactly)
+          alpha = ex2_approx(m - m_new);
+          d *= alpha;
+        }
         m = m_new;
 
         // P = exp2(S*coef - m) -> e4m3 (bit-identical to the reference, see attn.cu), d += sum(P)

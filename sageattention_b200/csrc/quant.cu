@@ -90,25 +90,7 @@ __global__ void __launch_bounds__(256) channel_stats_stage1(const T* __restrict_
   for (int i = 0; i < 8; ++i) { sum[i] = 0.f; mx[i] = -INFINITY; mn[i] = INFINITY; }
   const int r0 = chunk * kStatChunk;
   const int r1 = min(S, r0 + kStatChunk);
-  // eight independent 16-byte loads per thread in flight (32 KB per CTA) before the first is consumed; rows are folded in the
-  // same order as a plain loop, so the partial sums keep their bits
-  constexpr int kBatch = 8;
-  int r = r0 + tr;
-  for (; r + (kBatch - 1) * RPP < r1; r += kBatch * RPP) {
-    uint4 raw[kBatch];
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) raw[u] = *reinterpret_cast<const uint4*>(base + int64_t(r + u * RPP) * ss);
-#pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const T* e = reinterpret_cast<const T*>(&raw[u]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float f = to_f<T>(e[i]);
-        sum[i] += f; mx[i] = fmaxf(mx[i], f); mn[i] = fminf(mn[i], f);
-      }
-    }
-  }
-  for (; r < r1; r += RPP) {
+  for (int r = r0 + tr; r < r1; r += RPP) {
     float f[8];
     load8<T>(base + int64_t(r) * ss, f);
 #pragma unroll
@@ -170,8 +152,6 @@ struct QuantParams {
   int eps_after;      // Triton per-thread: scale = amax/127 + 1e-7
   // varlen (nullable): packed [T,H,D]
   const int32_t* cu; const int32_t* cu_scale;
-  // work list of the streaming kernel: item w -> tile w % n_tiles, head (w / n_tiles) % H, batch w / (n_tiles * H)
-  int n_tiles, n_items;
 };
 
 // Two 16-bit elements of one 32-bit word -> two floats (exact).
@@ -215,68 +195,30 @@ constexpr int kQfTriton = 1, kQfMean = 2, kQfSmScale = 4;   // FLAGS bits of qua
 //               half-integer (ties, or the 2.4e-5 error of x*RN(1/scale) against the IEEE quotient could matter);
 //               one |y - n| maximum per 8 elements decides, and those rare rows redo the exact reference sequence.
 // One 128-row tile of one (b,h).  `mean_bh`: the D per-channel means of this (b,h) (global or shared memory), or nullptr.
-// Geometry of one work item: false if the tile lies past the end of its (varlen) sequence.
-struct QuantTileGeom { int S; int64_t x_off, o_off; int scale_row0; };
-__device__ __forceinline__ bool quant_tile_geom(const QuantParams& p, const int tile, const int h, const int b, QuantTileGeom& g) {
-  g.S = p.S;
-  g.scale_row0 = 0;
-  if (p.cu != nullptr) {
-    const int t0 = p.cu[b];
-    g.S = p.cu[b + 1] - t0;
-    if (tile * 128 >= g.S) return false;
-    g.x_off = int64_t(t0) * p.xss + int64_t(h) * p.xsh;
-    g.o_off = int64_t(t0) * p.oss + int64_t(h) * p.osh;
-    g.scale_row0 = p.cu_scale[b];
-  } else {
-    g.x_off = int64_t(b) * p.xsb + int64_t(h) * p.xsh;
-    g.o_off = int64_t(b) * p.osb + int64_t(h) * p.osh;
-  }
-  return true;
-}
-
-__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* gsrc, bool valid) {
-  const int sz = valid ? 16 : 0;   // src-size 0: nothing is read, the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <typename T, int D, int MODE, int FLAGS>
-__device__ __forceinline__ void quant_int8_process(const QuantParams& p, const int tile, const int h, const int b, const T* mean_bh,
-                                                   const QuantTileGeom& geo, uint4 (&raw)[128 / (256 / (D / 8))]);
-
-// One 128-row tile with direct loads (the cluster kernel below calls this; the streaming kernel stages its loads itself).
 template <typename T, int D, int MODE, int FLAGS>
 __device__ __forceinline__ void quant_int8_tile(const QuantParams& p, const int tile, const int h, const int b, const T* mean_bh) {
-  constexpr int TPR = D / 8, RPP = 256 / TPR, NP = 128 / RPP;
-  QuantTileGeom geo;
-  if (!quant_tile_geom(p, tile, h, b, geo)) return;
-  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
-  const T* xb = reinterpret_cast<const T*>(p.x) + geo.x_off + tc * 8;
-  uint4 raw[NP];
-#pragma unroll
-  for (int ps = 0; ps < NP; ++ps) {
-    const int row = tile * 128 + ps * RPP + tr;
-    raw[ps] = make_uint4(0, 0, 0, 0);
-    if (row < geo.S) raw[ps] = *reinterpret_cast<const uint4*>(xb + int64_t(row) * p.xss);
-  }
-  quant_int8_process<T, D, MODE, FLAGS>(p, tile, h, b, mean_bh, geo, raw);
-}
-
-// raw[ps]: the 8 elements (tc*8 .. tc*8+7) of row ps*RPP + tr of the tile (zeros past the end of the sequence).
-template <typename T, int D, int MODE, int FLAGS>
-__device__ __forceinline__ void quant_int8_process(const QuantParams& p, const int tile, const int h, const int b, const T* mean_bh,
-                                                   const QuantTileGeom& geo, uint4 (&raw)[128 / (256 / (D / 8))]) {
   constexpr bool kTriton = (FLAGS & kQfTriton) != 0, kMean = (FLAGS & kQfMean) != 0, kSms = (FLAGS & kQfSmScale) != 0;
   constexpr int TPR = D / 8;
   constexpr int RPP = 256 / TPR;     // 16 (D=128) / 32 (D=64)
   constexpr int NP = 128 / RPP;      // passes: 8 / 4
   const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
-  const int S = geo.S;
-  const int scale_row0 = geo.scale_row0;
+  int S = p.S;
+  int64_t x_off, o_off;
+  int scale_row0 = 0;
   const bool varlen = p.cu != nullptr;
-  int8_t* ob = p.out + geo.o_off + tc * 8;
+  if (varlen) {
+    const int t0 = p.cu[b];
+    S = p.cu[b + 1] - t0;
+    if (tile * 128 >= S) return;
+    x_off = int64_t(t0) * p.xss + int64_t(h) * p.xsh;
+    o_off = int64_t(t0) * p.oss + int64_t(h) * p.osh;
+    scale_row0 = p.cu_scale[b];
+  } else {
+    x_off = int64_t(b) * p.xsb + int64_t(h) * p.xsh;
+    o_off = int64_t(b) * p.osb + int64_t(h) * p.osh;
+  }
+  const T* xb = reinterpret_cast<const T*>(p.x) + x_off + tc * 8;
+  int8_t* ob = p.out + o_off + tc * 8;
 
   uint64_t nmean2[4];   // (-mean[2w], -mean[2w+1])
   if constexpr (kMean) {
@@ -290,6 +232,13 @@ __device__ __forceinline__ void quant_int8_process(const QuantParams& p, const i
   __shared__ float s_scale[32];
   __shared__ float s_inv[32];   // RN(1/scale): fast path of the Triton-semantics division
 
+  uint4 raw[NP];
+#pragma unroll
+  for (int ps = 0; ps < NP; ++ps) {
+    const int row = tile * 128 + ps * RPP + tr;
+    raw[ps] = make_uint4(0, 0, 0, 0);
+    if (row < S) raw[ps] = *reinterpret_cast<const uint4*>(xb + int64_t(row) * p.xss);
+  }
   // transform of one word before the sm_scale multiply: x - mean (Triton: `k - km` rounds to the input dtype)
   auto centred = [&](uint32_t w, int wi, float& lo, float& hi) {
     cvt_pair<T>(w, lo, hi);
@@ -453,75 +402,12 @@ __device__ __forceinline__ void quant_int8_process(const QuantParams& p, const i
   }
 }
 
-// Streaming form: a fixed grid of CTAs (kQuantCtas per SM) walks the work list; the 16-byte loads of the next kQuantStages - 1 items
-// are in flight as cp.async copies into a shared-memory ring while item i is reduced, quantised and stored, so every CTA always
-// has at least one 128 x D tile (32 KB at D = 128) of reads outstanding — the one-tile-per-CTA form had none during its compute / store phases
-// and held 55-64 % of the copy bandwidth.  Every thread reads back exactly the bytes it copied itself: no barrier on the ring.
-#ifndef SAB_QUANT_STAGES
-#define SAB_QUANT_STAGES 2
-#endif
-#ifndef SAB_QUANT_CTAS
-#define SAB_QUANT_CTAS 3
-#endif
-constexpr int kQuantStages = SAB_QUANT_STAGES;   // ring depth: kQuantStages - 1 tiles of loads in flight per CTA
-constexpr int kQuantCtas = SAB_QUANT_CTAS;       // CTAs per SM (grid = kQuantCtas x SM count)
 template <typename T, int D, int MODE, int FLAGS>
-__global__ void __launch_bounds__(256, kQuantCtas) quant_int8_kernel(const QuantParams p) {
-  constexpr int TPR = D / 8, RPP = 256 / TPR, NP = 128 / RPP;
-  constexpr uint32_t kTileBytes = 128 * D * sizeof(T);
-  extern __shared__ __align__(16) uint8_t q_ring[];
-  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
-  const uint32_t my_slot = static_cast<uint32_t>(__cvta_generic_to_shared(q_ring)) + (tr * D + tc * 8) * sizeof(T);   // + stage * kTileBytes + ps * RPP * D * sizeof(T)
-
-  auto decode = [&](int w, int& tile, int& h, int& b) {
-    tile = w % p.n_tiles;
-    const int bh = w / p.n_tiles;
-    h = bh % p.H;
-    b = bh / p.H;
-  };
-  auto issue = [&](int w, int stage) {
-    int tile, h, b;
-    decode(w, tile, h, b);
-    QuantTileGeom geo;
-    if (quant_tile_geom(p, tile, h, b, geo)) {
-      const T* xb = reinterpret_cast<const T*>(p.x) + geo.x_off + tc * 8;
-#pragma unroll
-      for (int ps = 0; ps < NP; ++ps) {
-        const int row = tile * 128 + ps * RPP + tr;
-        const bool ok = row < geo.S;
-        cp_async16_zfill(my_slot + stage * kTileBytes + ps * (RPP * D * sizeof(T)), xb + (ok ? int64_t(row) * p.xss : 0), ok);
-      }
-    }
-  };
-
-  int w = blockIdx.x;
-  if (w >= p.n_items) return;
-  const int G = int(gridDim.x);
-#pragma unroll
-  for (int s = 0; s < kQuantStages - 1; ++s) {
-    if (w + s * G < p.n_items) issue(w + s * G, s);
-    cp_async_commit();
-  }
-  for (int it = 0; w < p.n_items; ++it, w += G) {
-    if (w + (kQuantStages - 1) * G < p.n_items) issue(w + (kQuantStages - 1) * G, (it + kQuantStages - 1) % kQuantStages);
-    cp_async_commit();          // (possibly empty) group: the wait below always leaves the newest kQuantStages - 1 pending
-    cp_async_wait<kQuantStages - 1>();
-    int tile, h, b;
-    decode(w, tile, h, b);
-    QuantTileGeom geo;
-    if (quant_tile_geom(p, tile, h, b, geo)) {
-      uint4 raw[NP];
-#pragma unroll
-      for (int ps = 0; ps < NP; ++ps)
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(raw[ps].x), "=r"(raw[ps].y), "=r"(raw[ps].z), "=r"(raw[ps].w)
-                     : "r"(my_slot + (it % kQuantStages) * kTileBytes + ps * uint32_t(RPP * D * sizeof(T))));
-      const T* mean_bh = nullptr;
-      if constexpr ((FLAGS & kQfMean) != 0) mean_bh = reinterpret_cast<const T*>(p.mean) + (int64_t(p.cu != nullptr ? 0 : b) * p.H + h) * D;
-      quant_int8_process<T, D, MODE, FLAGS>(p, tile, h, b, mean_bh, geo, raw);
-    }
-    __syncthreads();            // the scale scratch of quant_int8_process is reused by the next item
-  }
+__global__ void __launch_bounds__(256, 3) quant_int8_kernel(const QuantParams p) {
+  const int h = blockIdx.y, b = blockIdx.z;
+  const T* mean_bh = nullptr;
+  if constexpr ((FLAGS & kQfMean) != 0) mean_bh = reinterpret_cast<const T*>(p.mean) + (int64_t(p.cu != nullptr ? 0 : b) * p.H + h) * D;
+  quant_int8_tile<T, D, MODE, FLAGS>(p, blockIdx.x, h, b, mean_bh);
 }
 
 // =====================================================================================================
@@ -614,31 +500,36 @@ struct VQuantParams {
   const void* v; uint8_t* out; const float* recp; const float* vmean;
   int H, S; int64_t sb, sh, ss; int64_t s_pad; float scale_max;
   const int32_t* cu; const int32_t* cu_pad;
-  int n_tiles, n_items;   // work list of the streaming kernel
 };
 
-// VQuantParams work list (streaming kernel): item w -> tile w % n_tiles, head (w / n_tiles) % H, batch w / (n_tiles * H)
-struct VTileGeom { int S, tok0; int64_t col0; };
-__device__ __forceinline__ bool v_tile_geom(const VQuantParams& p, const int tile, const int b, VTileGeom& g) {
-  g.S = p.S;
-  g.tok0 = 0;
-  g.col0 = int64_t(tile) * 128;
-  if (p.cu != nullptr) {
-    g.tok0 = p.cu[b];
-    g.S = p.cu[b + 1] - g.tok0;
-    if (tile * 128 >= g.S) return false;
-    g.col0 += p.cu_pad[b];
-  }
-  return true;
-}
-
-// Transpose + quantise one staged tile: s_in[t][d] (row pitch D + 8 elements: conflict-free column reads) -> e4m3 [d][t].
-// thread -> (channel d, 32-token segment): 32 bytes = one full sector per thread
+// One 128-token tile.  recp_bh / vmean_bh: the D per-channel values of this (b,h) (global or shared memory; vmean may be null).
 template <typename T, int D>
-__device__ __forceinline__ void v_quant_transpose_staged(const VQuantParams& p, const int tile, const int h, const int b,
-                                                         const float* recp_bh, const float* vmean_bh, const VTileGeom& geo,
-                                                         const T (*s_in)[D + 8]) {
-  const int bh = (p.cu != nullptr ? 0 : b) * p.H + h;
+__device__ __forceinline__ void v_quant_transpose_tile(const VQuantParams& p, const int tile, const int h, const int b,
+                                                       const float* recp_bh, const float* vmean_bh) {
+  constexpr int TPR = D / 8;
+  constexpr int RPP = 256 / TPR;
+  int S = p.S, tok0 = 0;
+  int64_t col0 = int64_t(tile) * 128;
+  const bool varlen = p.cu != nullptr;
+  if (varlen) {
+    tok0 = p.cu[b];
+    S = p.cu[b + 1] - tok0;
+    if (tile * 128 >= S) return;
+    col0 += p.cu_pad[b];
+  }
+  __shared__ __align__(16) T s_in[128][D + 8];  // +8 elements: conflict-free column reads
+  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
+  const T* vb = reinterpret_cast<const T*>(p.v) + (varlen ? int64_t(tok0) * p.ss : int64_t(b) * p.sb) + int64_t(h) * p.sh + tc * 8;
+#pragma unroll
+  for (int r = tr; r < 128; r += RPP) {
+    const int row = tile * 128 + r;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (row < S) raw = *reinterpret_cast<const uint4*>(vb + int64_t(row) * p.ss);
+    *reinterpret_cast<uint4*>(&s_in[r][tc * 8]) = raw;
+  }
+  __syncthreads();
+  // thread -> (channel d, 32-token segment): 32 bytes = one full sector per thread
+  const int bh = (varlen ? 0 : b) * p.H + h;
   for (int task = threadIdx.x; task < D * 4; task += 256) {
     const int d = task % D, seg = task / D;
     const float recp = recp_bh[d];      // scale_max / amax
@@ -651,94 +542,22 @@ __device__ __forceinline__ void v_quant_transpose_staged(const VQuantParams& p, 
       for (int i = 0; i < 4; ++i) {
         const int t = seg * 32 + q4 * 4 + i;
         float x = to_f<T>(s_in[t][d]);
-        x = (tile * 128 + t < geo.S) ? (x - mean) * recp : 0.f;
+        x = (tile * 128 + t < S) ? (x - mean) * recp : 0.f;
         f[i] = x;
       }
       w[q4] = pack_e4m3x4_q(f[0], f[1], f[2], f[3]);
     }
-    uint8_t* dst = p.out + (int64_t(bh) * D + d) * p.s_pad + geo.col0 + seg * 32;
+    uint8_t* dst = p.out + (int64_t(bh) * D + d) * p.s_pad + col0 + seg * 32;
     reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
     reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
-// One 128-token tile with direct loads (cluster kernel).  recp_bh / vmean_bh: the D per-channel values of this (b,h) (global or
-// shared memory; vmean may be null).
 template <typename T, int D>
-__device__ __forceinline__ void v_quant_transpose_tile(const VQuantParams& p, const int tile, const int h, const int b,
-                                                       const float* recp_bh, const float* vmean_bh) {
-  constexpr int TPR = D / 8;
-  constexpr int RPP = 256 / TPR;
-  VTileGeom geo;
-  if (!v_tile_geom(p, tile, b, geo)) return;
-  __shared__ __align__(16) T s_in[128][D + 8];
-  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
-  const T* vb = reinterpret_cast<const T*>(p.v) + (p.cu != nullptr ? int64_t(geo.tok0) * p.ss : int64_t(b) * p.sb) + int64_t(h) * p.sh + tc * 8;
-#pragma unroll
-  for (int r = tr; r < 128; r += RPP) {
-    const int row = tile * 128 + r;
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    if (row < geo.S) raw = *reinterpret_cast<const uint4*>(vb + int64_t(row) * p.ss);
-    *reinterpret_cast<uint4*>(&s_in[r][tc * 8]) = raw;
-  }
-  __syncthreads();
-  v_quant_transpose_staged<T, D>(p, tile, h, b, recp_bh, vmean_bh, geo, s_in);
-}
-
-// Streaming form (same scheme as quant_int8_kernel): a fixed grid walks the work list, the next tile arrives by cp.async in the
-// other half of a two-stage ring while the current one is transposed and stored.
-template <typename T, int D>
-__global__ void __launch_bounds__(256, kQuantCtas) v_quant_transpose_kernel(const VQuantParams p) {
-  constexpr int TPR = D / 8, RPP = 256 / TPR;
-  constexpr uint32_t kPitch = (D + 8) * sizeof(T), kTileBytes = 128 * kPitch;
-  extern __shared__ __align__(16) uint8_t v_ring[];
-  const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
-  const uint32_t ring = static_cast<uint32_t>(__cvta_generic_to_shared(v_ring));
-
-  auto decode = [&](int w, int& tile, int& h, int& b) {
-    tile = w % p.n_tiles;
-    const int bh = w / p.n_tiles;
-    h = bh % p.H;
-    b = bh / p.H;
-  };
-  auto issue = [&](int w, int stage) {
-    int tile, h, b;
-    decode(w, tile, h, b);
-    VTileGeom geo;
-    if (v_tile_geom(p, tile, b, geo)) {
-      const T* vb = reinterpret_cast<const T*>(p.v) + (p.cu != nullptr ? int64_t(geo.tok0) * p.ss : int64_t(b) * p.sb) + int64_t(h) * p.sh + tc * 8;
-#pragma unroll
-      for (int r = tr; r < 128; r += RPP) {
-        const int row = tile * 128 + r;
-        const bool ok = row < geo.S;
-        cp_async16_zfill(ring + stage * kTileBytes + r * kPitch + tc * 16, vb + (ok ? int64_t(row) * p.ss : 0), ok);
-      }
-    }
-  };
-
-  int w = blockIdx.x;
-  if (w >= p.n_items) return;
-  const int G = int(gridDim.x);
-#pragma unroll
-  for (int s = 0; s < kQuantStages - 1; ++s) {
-    if (w + s * G < p.n_items) issue(w + s * G, s);
-    cp_async_commit();
-  }
-  for (int it = 0; w < p.n_items; ++it, w += G) {
-    if (w + (kQuantStages - 1) * G < p.n_items) issue(w + (kQuantStages - 1) * G, (it + kQuantStages - 1) % kQuantStages);
-    cp_async_commit();
-    cp_async_wait<kQuantStages - 1>();
-    __syncthreads();            // every thread's copies of this tile have landed
-    int tile, h, b;
-    decode(w, tile, h, b);
-    VTileGeom geo;
-    if (v_tile_geom(p, tile, b, geo)) {
-      const int64_t bh = int64_t(p.cu != nullptr ? 0 : b) * p.H + h;
-      v_quant_transpose_staged<T, D>(p, tile, h, b, p.recp + bh * D, p.vmean ? p.vmean + bh * D : nullptr, geo,
-                                     reinterpret_cast<const T(*)[D + 8]>(v_ring + (it % kQuantStages) * kTileBytes));
-    }
-    __syncthreads();            // this stage is refilled by the next iteration's copies
-  }
+__global__ void __launch_bounds__(256) v_quant_transpose_kernel(const VQuantParams p) {
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int64_t bh = int64_t(p.cu != nullptr ? 0 : b) * p.H + h;
+  v_quant_transpose_tile<T, D>(p, blockIdx.x, h, b, p.recp + bh * D, p.vmean ? p.vmean + bh * D : nullptr);
 }
 
 // Single-pass V path: per-channel |max| (+ mean for smooth_v) and the e4m3 quantisation + transpose in ONE launch, same cluster
@@ -875,37 +694,13 @@ static int run_stats(const void* x, int dtype, float* part, int B, int H, int S,
   return D == 128 ? launch_stats<__nv_bfloat16, 128>(x, part, B, H, S, sb, sh, ss, st) : launch_stats<__nv_bfloat16, 64>(x, part, B, H, S, sb, sh, ss, st);
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
-
-template <typename T, int D, int MODE, int FLAGS>
-static int launch_quant_m(QuantParams p, dim3 tiles, cudaStream_t st) {
-  // tiles = (128-row tiles per sequence, heads, batch / sequences): flattened into a work list walked by 3 CTAs per SM
-  constexpr int kSmem = kQuantStages * 128 * D * int(sizeof(T));
-  auto kern = quant_int8_kernel<T, D, MODE, FLAGS>;
-  static bool configured = false;
-  if (!configured) {
-    SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
-  }
-  p.n_tiles = int(tiles.x);
-  p.n_items = int(tiles.x * tiles.y * tiles.z);
-  const int grid = p.n_items < kQuantCtas * num_sms() ? p.n_items : kQuantCtas * num_sms();
-  kern<<<grid, 256, kSmem, st>>>(p);
-  SAB_CUDA_OK(cudaGetLastError());
-  return SAB_OK;
-}
 template <typename T, int D, int FLAGS>
 static int launch_quant_f(const QuantParams& p, int mode, dim3 grid, cudaStream_t st) {
-  if (mode == kGroupBlock) return launch_quant_m<T, D, kGroupBlock, FLAGS>(p, grid, st);
-  if (mode == kGroupThreadQ) return launch_quant_m<T, D, kGroupThreadQ, FLAGS>(p, grid, st);
-  return launch_quant_m<T, D, kGroupThreadK, FLAGS>(p, grid, st);
+  if (mode == kGroupBlock) quant_int8_kernel<T, D, kGroupBlock, FLAGS><<<grid, 256, 0, st>>>(p);
+  else if (mode == kGroupThreadQ) quant_int8_kernel<T, D, kGroupThreadQ, FLAGS><<<grid, 256, 0, st>>>(p);
+  else quant_int8_kernel<T, D, kGroupThreadK, FLAGS><<<grid, 256, 0, st>>>(p);
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
 }
 template <typename T, int D>
 static int launch_quant_t(const QuantParams& p, int mode, dim3 grid, cudaStream_t st) {
@@ -921,26 +716,6 @@ static int launch_quant_t(const QuantParams& p, int mode, dim3 grid, cudaStream_
     case 6: return launch_quant_f<T, D, 6>(p, mode, grid, st);
     default: return launch_quant_f<T, D, 7>(p, mode, grid, st);
   }
-}
-template <typename T, int D>
-static int launch_v_quant_t(VQuantParams p, dim3 tiles, cudaStream_t st) {
-  constexpr int kSmem = kQuantStages * 128 * (D + 8) * int(sizeof(T));
-  auto kern = v_quant_transpose_kernel<T, D>;
-  static bool configured = false;
-  if (!configured) {
-    SAB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    configured = true;
-  }
-  p.n_tiles = int(tiles.x);
-  p.n_items = int(tiles.x * tiles.y * tiles.z);
-  const int grid = p.n_items < kQuantCtas * num_sms() ? p.n_items : kQuantCtas * num_sms();
-  kern<<<grid, 256, kSmem, st>>>(p);
-  SAB_CUDA_OK(cudaGetLastError());
-  return SAB_OK;
-}
-static int launch_v_quant(const VQuantParams& p, int dtype, int D, dim3 tiles, cudaStream_t st) {
-  if (dtype == SAB_DTYPE_FP16) return D == 128 ? launch_v_quant_t<__half, 128>(p, tiles, st) : launch_v_quant_t<__half, 64>(p, tiles, st);
-  return D == 128 ? launch_v_quant_t<__nv_bfloat16, 128>(p, tiles, st) : launch_v_quant_t<__nv_bfloat16, 64>(p, tiles, st);
 }
 static int launch_quant(const QuantParams& p, int dtype, int D, int mode, dim3 grid, cudaStream_t st) {
   if (dtype == SAB_DTYPE_FP16) return D == 128 ? launch_quant_t<__half, 128>(p, mode, grid, st) : launch_quant_t<__half, 64>(p, mode, grid, st);
@@ -1071,7 +846,12 @@ extern "C" int sab_per_channel_fp8(const void* v, int dtype, uint8_t* v_fp8, flo
   p.v = v; p.out = v_fp8; p.recp = recp; p.vmean = v_mean; p.H = H; p.S = S;
   p.sb = stride_b; p.sh = stride_h; p.ss = stride_s; p.s_pad = s_pad; p.scale_max = scale_max; p.cu = cu_seqlens; p.cu_pad = cu_pad;
   dim3 grid(varlen ? (max_seqlen + 127) / 128 : int(s_pad / 128), H, varlen ? nseq : B);
-  return launch_v_quant(p, dtype, D, grid, s);
+#define SAB_VQ(T, DD) v_quant_transpose_kernel<T, DD><<<grid, 256, 0, s>>>(p)
+  if (dtype == SAB_DTYPE_FP16) { if (D == 128) SAB_VQ(__half, 128); else SAB_VQ(__half, 64); }
+  else { if (D == 128) SAB_VQ(__nv_bfloat16, 128); else SAB_VQ(__nv_bfloat16, 64); }
+#undef SAB_VQ
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
 }
 
 __global__ void amax_to_scale_kernel(const float* __restrict__ amax, float* __restrict__ scale, float* __restrict__ recp,
@@ -1114,7 +894,12 @@ extern "C" int sab_v_quant_with_amax(const void* v, int dtype, uint8_t* v_fp8, c
   p.v = v; p.out = v_fp8; p.recp = recp; p.vmean = nullptr; p.H = H; p.S = S;
   p.sb = stride_b; p.sh = stride_h; p.ss = stride_s; p.s_pad = s_pad; p.scale_max = scale_max; p.cu = nullptr; p.cu_pad = nullptr;
   dim3 grid(int(s_pad / 128), H, B);
-  return launch_v_quant(p, dtype, D, grid, s);
+#define SAB_VQ(T, DD) v_quant_transpose_kernel<T, DD><<<grid, 256, 0, s>>>(p)
+  if (dtype == SAB_DTYPE_FP16) { if (D == 128) SAB_VQ(__half, 128); else SAB_VQ(__half, 64); }
+  else { if (D == 128) SAB_VQ(__nv_bfloat16, 128); else SAB_VQ(__nv_bfloat16, 64); }
+#undef SAB_VQ
+  SAB_CUDA_OK(cudaGetLastError());
+  return SAB_OK;
 }
 
 extern "C" int sab_v_transpose_f16(const void* v, int dtype, void* v_f16t, int B, int H, int S, int D, int64_t stride_b,
