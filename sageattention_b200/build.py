@@ -8,7 +8,7 @@ import os, subprocess, sys, hashlib
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libsageattn_b200.so")
-SOURCES = ["attn.cu", "attn_hd64.cu", "attn_alt.cu", "quant.cu", "capi.cu"]
+SOURCES = ["attn.cu", "attn_hd64.cu", "attn_alt.cu", "attn_q4.cu", "quant.cu", "capi.cu"]
 HEADERS = ["ptx.cuh", "common.cuh", "attn_common.cuh", os.path.join("..", "..", "include", "sageattn_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

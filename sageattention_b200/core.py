@@ -112,7 +112,12 @@ def sageattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, tensor_layout: s
     """sageattention/core.py:79-157.  The reference dispatches on compute capability and raises on sm_100;
     here the single B200 backend is used with the reference's sm89 defaults (per-thread INT8, FP8 PV,
     "fp32+fp16" V range).  Unknown kwargs (attn_mask=, dropout_p=, scale=, ...) are accepted and ignored
-    exactly like the reference so SDPA monkey-patches keep working (example/cogvideox_infer.py:35)."""
+    exactly like the reference so SDPA monkey-patches keep working (example/cogvideox_infer.py:35).
+
+    The 2.25 V range of "fp32+fp16" exists in the reference to keep its fp16 PV accumulator from overflowing; this kernel
+    accumulates PV in fp32, so the range buys nothing here and is kept ONLY so that the quantised V bytes (and with them the
+    output) match what the reference's default sm89 dispatch produces.  Callers who prefer e4m3's full dynamic range for V call
+    sageattn_qk_int8_pv_fp8_cuda(..., pv_accum_dtype="fp32+fp32") (448 range, the reference's sm90 choice) at the same speed."""
     return sageattn_qk_int8_pv_fp8_cuda(q, k, v, tensor_layout=tensor_layout, is_causal=is_causal, sm_scale=sm_scale,
                                         return_lse=return_lse, pv_accum_dtype="fp32+fp16")
 

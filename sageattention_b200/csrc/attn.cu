@@ -579,10 +579,27 @@ static bool exact_max_mode() {
   return v == 1;
 }
 
+// attn_q4.cu: one CTA per SM, four softmax warpgroups, separate P buffers (SAB_ATTN_KERNEL=q4 / alt selects explicitly).
+template <bool kKT, typename OutT>
+int launch_attn_q4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
+                   cudaStream_t stream);
+#ifndef SAB_DEFAULT_Q4
+#define SAB_DEFAULT_Q4 0   // 1: attn_q4.cu is the head_dim-128 default, SAB_ATTN_KERNEL=alt selects attn_alt.cu
+#endif
+static bool q4_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SAB_ATTN_KERNEL");
+    v = (e != nullptr && e[0] == 'q') ? 1 : ((e != nullptr && e[0] == 'a') ? 0 : SAB_DEFAULT_Q4);
+  }
+  return v == 1;
+}
+
 template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false, bool kSeg = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        dim3 grid, cudaStream_t stream) {
   if constexpr (D == 128 && !kPV16) {   // also the fused-gather form: the producers poll p.seg_flags at run time
+    if (!exact_max_mode() && q4_mode() && p.dbg == nullptr) return launch_attn_q4<kKT, OutT>(tq, tk, tv, p, grid, stream);
     if (!exact_max_mode() && p.dbg == nullptr) return launch_attn_alt<D, kKT, OutT>(tq, tk, tv, p, grid, stream);
   }
   if constexpr (D == 64 && !kPV16) {
