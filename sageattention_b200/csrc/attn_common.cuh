@@ -69,6 +69,7 @@ struct AttnParams {
   int seg_heads;               // KV heads per flag group
   // dense outputs: byte-typed 4-D map of O (box 128 B x 128 rows, 128-byte swizzle) for the TMA-store epilogue of attn_alt.cu
   int o_tma;                   // 1: o_map is valid
+  int n_items;                 // attn_q4.cu: length of the work list (Q tiles x heads x batch)
   CUtensorMap o_map;
 };
 
