@@ -372,7 +372,7 @@ def run_ours(args):
         # denominator = 2 x the MEASURED cuBLAS bf16 burst figure.
         peak8 = 2.0 * pk["bf16_tflops"]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak8, "unit": "TFLOP/s", "frac": achieved / peak8,
-                "traffic": None, "kernel": "sab::sage_attn_lazy_kernel<128,true,bf16> (SAB_ATTN_KERNEL=exact: sab::sage_attn_fwd_kernel)", "kernel_ms": kms,
+                "traffic": None, "kernel": "sab::sage_attn_alt_kernel<128,true,bf16> (SAB_ATTN_KERNEL=exact: sab::sage_attn_fwd_kernel; =q4: sab::sage_attn_q4_kernel)", "kernel_ms": kms,
                 "peak_source": f"2 x bf16_tflops ({pk['bf16_tflops']}) of {pk_src} MEASURED_PEAKS.json",
                 # the same tensor core measured directly this round (tools/microbench/mma_peak.cu, profiles/r02_mma_peak.txt): back-to-back
                 # tcgen05.mma on all SMs, operands in smem/TMEM — the instruction-issue ceiling, above what any real kernel sustains

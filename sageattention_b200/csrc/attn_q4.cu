@@ -30,6 +30,10 @@
 namespace sab {
 
 constexpr int kQ4Threads = 640;
+#ifndef SAB_Q4_ITEMS
+#define SAB_Q4_ITEMS 1
+#endif
+constexpr int kQ4Items = SAB_Q4_ITEMS;   // consecutive work items (Q tiles of one head) per CTA
 constexpr uint32_t kQ4TmemCols = 512;
 #ifndef SAB_ALT_TAU
 #define SAB_ALT_TAU 4
@@ -152,7 +156,7 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // =============================== TMA producers: warp 16 Q + K ring, warp 19 V ring ===============================
       const bool is_k = warp == 16;
       if (lane == 0) {
-        for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+        for (int it = int(blockIdx.x) * kQ4Items; it < min(p.n_items, (int(blockIdx.x) + 1) * kQ4Items); ++it) {
           const Q4Item I = q4_decode(p, it);
           if (!I.valid) continue;
           if (I.n_kv > 0 && is_k) {
@@ -202,7 +206,7 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t dQ0 = make_smem_desc<128>(smem_u32(sQ));
       const uint64_t dK0 = make_smem_desc<128>(smem_u32(sK));
-      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {   // whole warp runs the loops (uniform control flow); one elected lane issues
+      for (int it = int(blockIdx.x) * kQ4Items; it < min(p.n_items, (int(blockIdx.x) + 1) * kQ4Items); ++it) {   // whole warp runs the loops (uniform control flow); one elected lane issues
         const Q4Item I = q4_decode(p, it);
         if (!I.valid) continue;
         if (I.n_kv > 0) {
@@ -235,7 +239,7 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       constexpr uint32_t idesc_pv = make_idesc(1, 0, 0, BM, D);    // f32 <- e4m3 x e4m3, 128 x 128
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t dV0 = make_smem_desc<64>(smem_u32(sV));
-      for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+      for (int it = int(blockIdx.x) * kQ4Items; it < min(p.n_items, (int(blockIdx.x) + 1) * kQ4Items); ++it) {
         const Q4Item I = q4_decode(p, it);
         if (!I.valid) continue;
         // O is single-buffered: the epilogue of the previous item that used it (n_kv > 0) must have loaded it.  Items without key
@@ -276,9 +280,28 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     //   * m_full[(g-1)&3] and pv_done[(g-1)&3] by the owner of tile g (same item): tile g+3 of that buffer needs m(g) / P(g) from
     //     this warpgroup or, in the next item, this warpgroup's arrival at the item's epilogue barrier (not ahead); tile g-5 was
     //     completed before this warpgroup's tile g-4 needed it, or before the previous item's epilogue barrier (not behind).
-    for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
+    // FULLY UNROLLED: with a back edge around the tile body ptxas spilled 64-88 bytes per thread inside the exponential loop (and 203 KB of
+    // shared memory leave almost no L1 for local memory): 966 instead of 1475 TFLOP/s.  A single pass over the body compiles clean,
+    // so the CTA takes a FIXED, small number of items and the item loop disappears at compile time.
+#pragma unroll
+    for (int u = 0; u < kQ4Items; ++u) {
+      const int it = int(blockIdx.x) * kQ4Items + u;
+      if (it >= p.n_items) break;
+      // Each copy of the item body derives its addresses and thread geometry from opaque values of its own: shared between the
+      // copies (common sub-expressions) they stayed live across the tile bodies and were spilled inside the exponential loop.
+      uint8_t* sm = smem;
+      uint32_t c_tid = threadIdx.x, c_tmem_base = tmem_base;
+      asm volatile("" : "+l"(sm), "+r"(c_tid), "+r"(c_tmem_base));
+#define Q4_LOCAL(T, name) T const c_##name = reinterpret_cast<T>(sm + (reinterpret_cast<uint8_t*>(name) - smem))
+      Q4_LOCAL(uint64_t*, s_full); Q4_LOCAL(uint64_t*, s_free); Q4_LOCAL(uint64_t*, p_full); Q4_LOCAL(uint64_t*, pv_done);
+      Q4_LOCAL(uint64_t*, m_full); Q4_LOCAL(uint64_t*, o_free); Q4_LOCAL(float*, s_m); Q4_LOCAL(float*, s_x); Q4_LOCAL(uint8_t*, sStage);
+#undef Q4_LOCAL
+      const int c_wg = int(c_tid >> 7);
+      const int c_row = int(c_tid & 127u);
+      const uint32_t c_lane_off = (c_tid & 96u) << 16;
+      const uint32_t c_tO = c_tmem_base + c_lane_off + 384;
       // Only what the tile loop needs stays live across it (the warpgroup runs at 104 registers); the epilogue decodes the item again.
-      int n_kv, kv_len, cq;       // cq: causal bound of this thread's row (key index < cq + row is visible); "infinite" when not causal
+      int n_kv, kv_len, cq;       // cq: causal bound of this thread's c_row (key index < cq + c_row is visible); "infinite" when not causal
       const float* ks_ptr;
       float qss;
       {
@@ -288,8 +311,8 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         kv_len = I.kv_len;
         cq = p.causal ? p.causal_q_offset + I.qt * BM + 1 : (1 << 30);
         int q_idx = (I.q_blk0 + I.qt) * p.q_mult;
-        if (p.q_gran == SAB_GRAN_PER_WARP) q_idx += row >> 5;
-        if (p.q_gran == SAB_GRAN_PER_THREAD) q_idx += (row >> 5) * 8 + (row & 7);
+        if (p.q_gran == SAB_GRAN_PER_WARP) q_idx += c_row >> 5;
+        if (p.q_gran == SAB_GRAN_PER_THREAD) q_idx += (c_row >> 5) * 8 + (c_row & 7);
         const float* qs_base = p.q_scale + (varlen ? int64_t(I.h) : (int64_t(I.b) * p.Hq + I.h) * p.qs_stride_bh);
         const float* ks_base = p.k_scale + (varlen ? int64_t(I.hk) : (int64_t(I.b) * p.Hkv + I.hk) * p.ks_stride_bh);
         ks_ptr = ks_base + int64_t(I.k_blk0) * NG * p.ks_stride_idx;
@@ -299,11 +322,11 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float m_own = kMaskValue;   // m of this warpgroup's latest tile of the item: the reference its partial sum d is relative to
       float d = 0.f;              // sum of P over THIS warpgroup's tiles of the item, relative to m_own
 
-      for (int j = int((uint32_t(wg) - g0) & 3u); j < n_kv; j += NW) {
+      for (int j = int((uint32_t(c_wg) - g0) & 3u); j < n_kv; j += NW) {
         const uint32_t g = g0 + j;
-        const int bf = wg;          // == g & 3
-        const uint32_t tS = tmem_base + lane_off + bf * BN;
-        const uint32_t tP = tmem_base + lane_off + 256 + bf * 16;
+        const int bf = c_wg;          // == g & 3
+        const uint32_t tS = c_tmem_base + c_lane_off + bf * BN;
+        const uint32_t tP = c_tmem_base + c_lane_off + 256 + bf * 16;
         float coef[NG];
         if constexpr (kKT) {
           if (p.ks_vec4) {   // dense: the four per-thread scales of a key tile are one aligned 16-byte word
@@ -316,15 +339,15 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         } else {
           coef[0] = ks_ptr[int64_t(j) * p.ks_stride_idx] * qss;
         }
-        const int limit = min(kv_len, cq + row) - j * BN;
+        const int limit = min(kv_len, cq + c_row) - j * BN;
         const bool masked_tile = (kv_len - j * BN < BN) || ((j + 1) * BN > cq);
 
-        mbar_wait_wd(s_full + bf, (g >> 2) & 1u);
+        mbar_wait_wd(c_s_full + bf, (g >> 2) & 1u);
         tc_fence_after();
 
         auto tile = [&](auto masked_tag) {
           constexpr bool MASKED = decltype(masked_tag)::value;
-          // ---- pass 1: row max, streamed in two 32-column loads
+          // ---- pass 1: c_row max, streamed in two 32-column loads
           int pm[4] = {kIntSentinel, kIntSentinel, kIntSentinel, kIntSentinel};
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
@@ -350,13 +373,13 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if constexpr (MASKED) c = (v == kIntSentinel) ? kMaskValue : c;
             mx = fmaxf(mx, c);
           }
-          // ---- the running max: m(g-1) comes from warpgroup (g-1) & 3, which published it right after ITS row max.  Slot reuse:
+          // ---- the running max: m(g-1) comes from warpgroup (g-1) & 3, which published it right after ITS c_row max.  Slot reuse:
           //      I overwrite slot g & 3 (m(g-4)), last read by the owner of tile g-3 before it published m(g-3); m(g-1), which I
           //      wait for here, came after m(g-2), after m(g-3) (or the previous item's epilogue barrier lies in between).
           float m_prev = kMaskValue;
           if (j > 0) {
-            mbar_wait_wd(m_full + ((g - 1) & 3), ((g - 1) >> 2) & 1u);
-            m_prev = s_m[((g - 1) & 3) * BM + row];
+            mbar_wait_wd(c_m_full + ((g - 1) & 3), ((g - 1) >> 2) & 1u);
+            m_prev = c_s_m[((g - 1) & 3) * BM + c_row];
           }
 #if SAB_ALT_TAU > 0
           const float m_true = fmaxf(m_prev, mx - (kFp8Offset - float(SAB_ALT_TAU)));
@@ -364,8 +387,8 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #else
           const float m_new = fmaxf(m_prev, mx - kFp8Offset);   // update_mdo, attn_utils.cuh:377-396
 #endif
-          s_m[bf * BM + row] = m_new;
-          mbar_arrive(m_full + bf);
+          c_s_m[bf * BM + c_row] = m_new;
+          mbar_arrive(c_m_full + bf);
           float alpha_o = 1.0f;                                   // rescale of O before PV(g): consecutive tiles
           if (__any_sync(0xffffffffu, (m_new != m_prev) | (m_new != m_own))) {   // lazy max: rare after the first tiles (ex2(0) = 1)
             alpha_o = ex2_approx(m_prev - m_new);
@@ -386,7 +409,7 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tc_wait_ld();
             if (hf == 1) {             // last read of S(g): the QK issuer may overwrite the buffer with S(g+4)
               tc_fence_before();
-              mbar_arrive(s_free + bf);
+              mbar_arrive(c_s_free + bf);
             }
             uint32_t pk[8];
 #pragma unroll
@@ -410,7 +433,7 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               pk[w] = pack_e4m3x4(e[0], e[1], e[2], e[3]);
             }
             if (hf == 0 && g >= NW) {   // P buffer g & 3 still holds P(g-4) until PV(g-4) has retired
-              mbar_wait_wd(pv_done + bf, ((g >> 2) - 1) & 1u);
+              mbar_wait_wd(c_pv_done + bf, ((g >> 2) - 1) & 1u);
               tc_fence_after();
             }
             tmem_st8(tP + 8 * hf, pk);
@@ -422,15 +445,15 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             d += (a0 + a1) + (a2 + a3);
           }
 
-          // ---- in-line correction of this row of O, when any row of the warp moved its max: needs PV(g-1) accumulated
+          // ---- in-line correction of this c_row of O, when any c_row of the warp moved its max: needs PV(g-1) accumulated
           if (j > 0 && __any_sync(0xffffffffu, alpha_o != 1.0f)) {
-            mbar_wait_wd(pv_done + ((g - 1) & 3), ((g - 1) >> 2) & 1u);
+            mbar_wait_wd(c_pv_done + ((g - 1) & 3), ((g - 1) >> 2) & 1u);
             tc_fence_after();
             const uint64_t alpha2 = pack_f2(alpha_o, alpha_o);
 #pragma unroll
             for (int ch = 0; ch < D / 32; ++ch) {
               uint32_t r[32];
-              tmem_ld32(tO + ch * 32, r);
+              tmem_ld32(c_tO + ch * 32, r);
               tc_wait_ld();
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
@@ -439,7 +462,7 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 r[i] = __float_as_uint(lo);
                 r[i + 1] = __float_as_uint(hi);
               }
-              tmem_st32(tO + ch * 32, r);
+              tmem_st32(c_tO + ch * 32, r);
             }
           }
         };
@@ -448,22 +471,22 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
         tc_wait_st();
         tc_fence_before();
-        mbar_arrive(p_full + bf);
+        mbar_arrive(c_p_full + bf);
       }
 
       // ---- epilogue of the item: combine the four partial sums relative to the final max, then each warpgroup writes OC columns
       // (opaque copies: the item is decoded again and the epilogue's address arithmetic is kept from being hoisted out of the item
       //  loop — either would stay live across the tile loop, which runs at 104 registers)
-      int it_e = it, row_e = row, wg_e = wg;
+      int it_e = it, row_e = c_row, wg_e = c_wg;
       asm volatile("" : "+r"(it_e), "+r"(row_e), "+r"(wg_e));
       const Q4Item I = q4_decode(p, it_e);
       const int qt = I.qt, h = I.h, b = I.b, hk = I.hk;
       const int q_row = qt * BM + row_e;
-      float* sx = s_x + (vi & 1) * (2 * NW * BM);   // double-buffered: a fast warpgroup may already deposit the next item's sums
+      float* sx = c_s_x + (vi & 1) * (2 * NW * BM);   // double-buffered: a fast warpgroup may already deposit the next item's sums
       sx[(wg_e * 2 + 0) * BM + row_e] = d;
       sx[(wg_e * 2 + 1) * BM + row_e] = m_own;
       if (n_kv > 0 && uint32_t(wg_e) == ((g0 + n_kv - 1) & 3u)) {   // owner of the last tile: O is final once its PV has retired
-        mbar_wait_wd(pv_done + wg_e, ((g0 + n_kv - 1) >> 2) & 1u);
+        mbar_wait_wd(c_pv_done + wg_e, ((g0 + n_kv - 1) >> 2) & 1u);
         tc_fence_after();
       }
       tc_fence_before();
@@ -478,11 +501,11 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
       uint32_t r[32];
       if (n_kv > 0) {
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(row_e & ~31) << 16) + 384 + wg_e * OC, r);
+        tmem_ld32(c_tmem_base + (static_cast<uint32_t>(row_e & ~31) << 16) + 384 + wg_e * OC, r);
         tc_wait_ld();
       }
       tc_fence_before();
-      if (n_kv > 0) mbar_arrive(o_free);   // the PV issuer may start the next item (O is overwritten by its first PV)
+      if (n_kv > 0) mbar_arrive(c_o_free);   // the PV issuer may start the next item (O is overwritten by its first PV)
 
       const bool row_ok = q_row < I.q_len;
       // Dense outputs leave through TMA: a PAIR of warpgroups stages its [128 rows][128 B] half of the tile (128-byte swizzle;
@@ -490,7 +513,7 @@ sage_attn_q4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const bool use_tma = kTmaStoreEpilogue && p.o_tma != 0;
       static_assert(OC * sizeof(OutT) == 64, "staging: 128 rows x 128 bytes per warpgroup pair");
       const int pair = wg_e >> 1;
-      uint8_t* stage = sStage + pair * (BM * 128);
+      uint8_t* stage = c_sStage + pair * (BM * 128);
       const uint32_t stage_row = smem_u32(stage) + row_e * 128;
       const float* vs = p.v_scale ? p.v_scale + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D + wg_e * OC : nullptr;
       const float* vm = p.v_mean ? p.v_mean + (int64_t(varlen ? 0 : b) * p.Hkv + hk) * D + wg_e * OC : nullptr;
@@ -565,13 +588,7 @@ int launch_attn_q4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
   }
   AttnParams p = p_in;
   p.n_items = int(grid.x * grid.y * grid.z);
-  int ctas = p.n_items < n_sm ? p.n_items : n_sm;
-  static int cap = -1;            // SAB_Q4_CTAS=n caps the grid (tests: several items per CTA also on small problems)
-  if (cap < 0) {
-    const char* e = getenv("SAB_Q4_CTAS");
-    cap = e ? atoi(e) : 0;
-  }
-  if (cap > 0 && ctas > cap) ctas = cap;
+  const int ctas = (p.n_items + kQ4Items - 1) / kQ4Items;
   kern<<<ctas, kQ4Threads, smem, stream>>>(tq, tk, tv, p);
   SAB_CUDA_OK(cudaGetLastError());
   return SAB_OK;

@@ -12,6 +12,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "short":
     shapes = shapes[:1]
 if len(sys.argv) > 1 and sys.argv[1] == "short2":
     shapes = shapes[:3]
+if len(sys.argv) > 1 and sys.argv[1] == "long":     # sequence-length sweep at head_dim 128 (kernel only)
+    shapes = [(2, 32, 8192, 128, 0, "per_thread"), (1, 32, 16384, 128, 0, "per_thread"), (1, 32, 32768, 128, 0, "per_thread"),
+              (1, 32, 16384, 128, 1, "per_thread"), (1, 32, 32768, 128, 1, "per_thread")]
 out = []
 for (B, H, S, D, causal, gran) in shapes:
     torch.manual_seed(0)
@@ -32,7 +35,7 @@ for (B, H, S, D, causal, gran) in shapes:
     ms = e0.elapsed_time(e1) / n
     fl = 4.0 * B * H * S * S * D / (2 if causal else 1)
     out.append(f"D{D} S{S} c{causal} {gran}: {fl / ms / 1e9:.0f}")
-if not (len(sys.argv) > 1 and sys.argv[1].startswith("short")):
+if not (len(sys.argv) > 1 and (sys.argv[1].startswith("short") or sys.argv[1] == "long")):
     # BASELINE configs[3]: sageattn_varlen, GQA Hq=32 / Hkv=8, hd=128, sequence lengths 512..16384 (whole call: quantisation + FP16-PV kernel)
     lens = [512, 1024, 2048, 4096, 8192, 16384]
     g = torch.Generator().manual_seed(0)
