@@ -1,4 +1,4 @@
-// Fused INT8-QK / FP8-PV attention for sm_100a (B200), head_dim 128: ONE persistent CTA per SM, FOUR softmax warpgroups.
+// Fused INT8-QK / FP8-PV attention for sm_100a (B200), head_dim 128: ONE CTA per SM, FOUR softmax warpgroups.
 //
 // attn_alt.cu (two CTAs per SM, two softmax warpgroups each) leaves the MUFU 31 % idle: with 256 TMEM columns per CTA the e4m3
 // P(j) has to alias its own S buffer, so QK(j+2) cannot be issued before PV(j) has consumed P(j), and every warpgroup waits
@@ -11,17 +11,18 @@
 // one for QK^T (waits s_free / K tiles, commits s_full), one for PV (waits p_full / V tiles, commits pv_done) — and K and V
 // travel in separate rings with their own producers, because K(g+4) is consumed about four tiles before V(g).
 //
-// PERSISTENT: the first (one CTA per Q tile) form measured the same as attn_alt.cu — ~630 instead of 757 cycles per key tile in
-// steady state, but ~16 K cycles of launch, prologue, pipeline fill and epilogue per CTA that nothing hides with one CTA per SM
-// (profiles/r02_q4_first_contact.log).  So gridDim.x = #SMs CTAs walk the work list (item = Q tile of one (batch, head), the
-// Q tiles of a head adjacent so that its K/V stay in L2; causal: heaviest first) with a stride of gridDim.x, and the key tiles of
-// all items of a CTA form ONE stream g = 0, 1, 2, ...: buffers, warpgroup assignment and mbarrier parities run on g across item
-// boundaries, so nothing is re-initialised and the QK^T issuer runs ahead into the next item (Q is double-buffered) while the
-// softmax warpgroups finish the previous one.  Only O is single: the first PV of an item waits until the epilogue of the previous
-// item has loaded O from TMEM (`o_free`).
+// Measured (profiles/r02_q4_first_contact.log): +2-3 % over attn_alt.cu at S = 16K-32K, -2 % at S = 8K — the S wait this design
+// removes is not where the idle MUFU time goes.  OPT-IN (SAB_ATTN_KERNEL=q4); the product kernel is attn_alt.cu.
+//
+// A CTA takes SAB_Q4_ITEMS consecutive work items (item = Q tile of one (batch, head); default 1).  The code is written for a stream
+// of items: the key tiles of all items of a CTA form ONE sequence g = 0, 1, 2, ...; buffers, warpgroup assignment and mbarrier
+// parities run on g across item boundaries, the QK^T issuer runs ahead into the next item (Q is double-buffered), and only O is
+// single — the first PV of an item waits until the epilogue of the previous item has loaded O from TMEM (`o_free`).  That form is
+// correct (also as a persistent grid of #SMs CTAs walking the whole list) but slow: with more than one copy of the tile body ptxas
+// spills 64-88 bytes per thread inside the exponential loop, and 150-200 KB of shared memory leave almost no L1 for local memory.
 // Everything on the softmax side is attn_alt.cu's: one thread per row and tile, lazy running max (SAB_ALT_TAU), the running max
 // chained through shared memory (`m_full`), in-line O rescale (rare), partial row sums per warpgroup combined in the epilogue,
-// TMA-store epilogue (own staging buffer: the K ring is busy with the next item).
+// TMA-store epilogue (own staging buffer: with several items per CTA the K ring is busy with the next item).
 // 640 threads: warps 0-15 softmax (104 registers), 16 Q + K producer, 17 QK issuer + TMEM allocator, 18 PV issuer, 19 V producer
 // (64 registers): 512 x 104 + 128 x 64 = 640 x 96, the CTA's register pool.
 #include <cstdlib>
