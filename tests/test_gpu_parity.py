@@ -417,6 +417,40 @@ def test_exact_max_kernel_matches_reference_kernel_bits():
     print(p.stdout[-300:])
 
 
+def test_q4_kernel_opt_in_matches_the_product_kernel():
+    """SAB_ATTN_KERNEL=q4 selects csrc/attn_q4.cu at head_dim 128 (one CTA per SM, four softmax warpgroups, separate P buffers in
+    TMEM): same lazy-max arithmetic as the product kernel — P, m and the PV accumulation order are identical, only the row sum is
+    combined from four partial sums instead of two — so it has to pass the product kernel's checks against the real reference
+    kernel, and agree with the product kernel itself to an output ulp.  Subprocess: the kernel choice is read once per process."""
+    import subprocess, sys
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import torch, sageattention_b200 as sab\nfrom sageattention_b200 import ops\nfrom oracle import sage_oracle as O\n"
+            "import test_gpu_parity as T\nr = T._check_vs_real_reference_kernel(sab, ops, O)\nprint('VSREF', r)\n"
+            "outs = []\n"
+            "for (B, H, Hk, S, causal, gran, dt) in [(2, 4, 2, 1000, True, 'per_thread', torch.bfloat16), (1, 40, 40, 2048, False, 'per_warp', torch.float16),\n"
+            "                                        (1, 2, 2, 77, False, 'per_thread', torch.float16)]:\n"
+            "    g = torch.Generator(device='cuda').manual_seed(S)\n"
+            "    q = torch.randn(B, H, S, 128, device='cuda', generator=g).to(dt); k = torch.randn(B, Hk, S, 128, device='cuda', generator=g).to(dt)\n"
+            "    v = torch.randn(B, Hk, S, 128, device='cuda', generator=g).to(dt)\n"
+            "    o, lse = sab.sageattn_qk_int8_pv_fp8_cuda(q, k, v, is_causal=causal, qk_quant_gran=gran, return_lse=True)\n"
+            "    outs.append((o.float().cpu(), lse.cpu()))\n"
+            "torch.save(outs, sys.argv[1])\nprint('SAVED')\n" % (ROOT, os.path.join(ROOT, "tests")))
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for kern in ("q4", "alt"):
+            path = os.path.join(td, kern + ".pt")
+            p = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, SAB_ATTN_KERNEL=kern), capture_output=True, text=True, timeout=600)
+            assert p.returncode == 0 and "VSREF" in p.stdout and "SAVED" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+            res[kern] = torch.load(path)
+    for (oq, lq), (oa, la) in zip(res["q4"], res["alt"]):
+        assert (oq - oa).abs().max().item() <= 2 ** -7 * max(1.0, oa.abs().max().item())       # one bf16 ulp of the largest output
+        assert (oq != oa).float().mean().item() < 0.05
+        assert (lq - la).abs().max().item() < 1e-5
+
+
 def test_fp16_pv_cuda_entry_vs_real_reference_kernel_and_oracle(env):
     """sageattn_qk_int8_pv_fp16_cuda (core.py:451-633): per-warp / per-thread INT8 Q,K + FP16 P and V.  Against the REAL
     reference sm80 kernel (`qk_int8_sv_f16_accum_f32_attn`, csrc/qattn/qk_int_sv_f16_cuda_sm80.cu built for sm_100a) on the same

@@ -25,6 +25,8 @@ VARIANTS = {
 }
 ENVS = {}   # per-variant environment (e.g. {"exact": {"SAB_ATTN_KERNEL": "exact"}} selects the exact-max kernels of any build)
 ENVS["exact"] = {"SAB_ATTN_KERNEL": "exact"}
+ENVS["q4"] = {"SAB_ATTN_KERNEL": "q4"}
+VARIANTS["q4"] = ([], "attn_q4.cu: one CTA per SM, four softmax warpgroups, separate P buffers (head_dim 128) of the product build")
 VARIANTS["exact"] = ([], "the exact-max kernels (attn.cu / attn_hd64.cu kLazy=false) of the product build")
 PARITY_K = "attention_vs_oracle or full_size_config1 or api_behaviour"
 
