@@ -421,7 +421,9 @@ def test_q4_kernel_opt_in_matches_the_product_kernel():
     """SAB_ATTN_KERNEL=q4 selects csrc/attn_q4.cu at head_dim 128 (one CTA per SM, four softmax warpgroups, separate P buffers in
     TMEM): same lazy-max arithmetic as the product kernel — P, m and the PV accumulation order are identical, only the row sum is
     combined from four partial sums instead of two — so it has to pass the product kernel's checks against the real reference
-    kernel, and agree with the product kernel itself to an output ulp.  Subprocess: the kernel choice is read once per process."""
+    kernel, and agree with the product kernel itself to an output ulp.  The last shape (256 key tiles, 256 CTAs) is one the default
+    dispatch gives to attn_q4.cu (csrc/attn.cu prefer_q4: long keys and a grid that quantises badly into 2 x #SMs slots).
+    Subprocess: the kernel choice is read once per process."""
     import subprocess, sys
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
@@ -430,7 +432,7 @@ def test_q4_kernel_opt_in_matches_the_product_kernel():
             "import test_gpu_parity as T\nr = T._check_vs_real_reference_kernel(sab, ops, O)\nprint('VSREF', r)\n"
             "outs = []\n"
             "for (B, H, Hk, S, causal, gran, dt) in [(2, 4, 2, 1000, True, 'per_thread', torch.bfloat16), (1, 40, 40, 2048, False, 'per_warp', torch.float16),\n"
-            "                                        (1, 2, 2, 77, False, 'per_thread', torch.float16)]:\n"
+            "                                        (1, 2, 2, 77, False, 'per_thread', torch.float16), (1, 2, 2, 16384, False, 'per_thread', torch.bfloat16)]:\n"
             "    g = torch.Generator(device='cuda').manual_seed(S)\n"
             "    q = torch.randn(B, H, S, 128, device='cuda', generator=g).to(dt); k = torch.randn(B, Hk, S, 128, device='cuda', generator=g).to(dt)\n"
             "    v = torch.randn(B, Hk, S, 128, device='cuda', generator=g).to(dt)\n"
