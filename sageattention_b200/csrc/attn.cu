@@ -583,32 +583,16 @@ static bool exact_max_mode() {
 template <bool kKT, typename OutT>
 int launch_attn_q4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, dim3 grid,
                    cudaStream_t stream);
-// Which head_dim-128 kernel: SAB_ATTN_KERNEL=alt / q4 forces one; otherwise attn_alt.cu unless the launch has long key sequences
-// AND its grid quantises badly into attn_alt.cu's 2 x #SMs slots.  attn_q4.cu runs one CTA per SM at about attn_alt.cu's per-SM
-// throughput (+2-3 % from 256 key tiles on, profiles/r02_q4_first_contact.log), so its waves are half as long: a sequence-parallel
-// rank at N = 8 (960 CTAs of 512 key tiles: 3.24 waves of 296 against 6.5 waves of 148) loses 7 % instead of 19 % in the last wave.
-static int q4_mode_env() {   // -1: not forced
-  static int v = -2;
-  if (v == -2) {
+// Which head_dim-128 kernel: attn_alt.cu unless SAB_ATTN_KERNEL=q4.  A length / wave-quantisation heuristic that gave long key
+// sequences to attn_q4.cu (kernel-only +2-3 % from 256 key tiles on, and waves half as long) was measured on the 2-GPU sequence-
+// parallel bench and LOST 5 % (profiles/r02_bench_n2_q4_dispatch.json: 2490 against 2625 TFLOP/s), so the choice stays explicit.
+static bool prefer_q4(const AttnParams&, dim3) {
+  static int v = -1;
+  if (v < 0) {
     const char* e = getenv("SAB_ATTN_KERNEL");
-    v = (e != nullptr && e[0] == 'q') ? 1 : ((e != nullptr && e[0] == 'a') ? 0 : -1);
+    v = (e != nullptr && e[0] == 'q') ? 1 : 0;
   }
-  return v;
-}
-static bool prefer_q4(const AttnParams& p, dim3 grid) {
-  const int forced = q4_mode_env();
-  if (forced >= 0) return forced == 1;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
-  }
-  const long n = long(grid.x) * grid.y * grid.z;
-  const int n_kv = (p.Sk + BN - 1) / BN;
-  if (p.cu_q != nullptr || n < n_sm || n_kv < (p.causal ? 512 : 256)) return false;
-  const long waves_alt = (n + 2 * n_sm - 1) / (2 * n_sm);   // each at half speed (two CTAs share an SM)
-  const long waves_q4 = (n + n_sm - 1) / n_sm;
-  return waves_q4 * 98 < 2 * waves_alt * 100;
+  return v == 1;
 }
 
 template <int D, bool kKT, typename OutT, bool kPV16, bool kMask = false, bool kSeg = false>

@@ -421,8 +421,7 @@ def test_q4_kernel_opt_in_matches_the_product_kernel():
     """SAB_ATTN_KERNEL=q4 selects csrc/attn_q4.cu at head_dim 128 (one CTA per SM, four softmax warpgroups, separate P buffers in
     TMEM): same lazy-max arithmetic as the product kernel — P, m and the PV accumulation order are identical, only the row sum is
     combined from four partial sums instead of two — so it has to pass the product kernel's checks against the real reference
-    kernel, and agree with the product kernel itself to an output ulp.  The last shape (256 key tiles, 256 CTAs) is one the default
-    dispatch gives to attn_q4.cu (csrc/attn.cu prefer_q4: long keys and a grid that quantises badly into 2 x #SMs slots).
+    kernel, and agree with the product kernel itself to an output ulp (the last shape has 256 key tiles per CTA).
     Subprocess: the kernel choice is read once per process."""
     import subprocess, sys
     if not torch.cuda.is_available():
