@@ -19,8 +19,11 @@
 //     P keeps e4m3's relative precision (a floating format); only the tail below 2^-9 is cut 2^tau earlier.  P is therefore a
 //     different rounding realisation than the reference kernel's (same accuracy against exact attention, tests/test_gpu_parity.py);
 //     SAB_ATTN_KERNEL=exact selects the exact-max kernel of attn.cu.
-// 384 threads, registers 96 / 96 / 48 via setmaxnreg; no correction warpgroup.
-// Measured (B200, hd128 S=8192 non-causal, kernel only): 1307 TFLOP/s at tau = 0, 1438 at tau = 3, 1452 at tau = 4 (exact kernel: 1277).
+// 384 threads, registers 96 / 96 / 48 via setmaxnreg; no correction warpgroup.  Epilogue: each warpgroup stages its 64 output columns
+// in the idle K ring (128-byte swizzle) and one thread issues a TMA bulk tensor store (dense outputs; packed varlen rows are stored directly).
+// Measured (B200, hd128 S=8192 non-causal, kernel only): 1307 TFLOP/s at tau = 0, 1438 at tau = 3, 1452 at tau = 4 (exact kernel: 1277);
+// 1492 with the TMA-store epilogue, one float4 K-scale load per tile and the rescale ex2 skipped when the max did not move
+// (profiles/r02_bench_n1.json: 0.425 of the 8-bit denominator, XU pipe 70 % busy).
 #include "attn_common.cuh"
 
 namespace sab {
