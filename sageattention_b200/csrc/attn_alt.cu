@@ -33,7 +33,7 @@ constexpr int kAltThreads = 384;   // warpgroups: 0 = softmax of even key tiles,
 #define SAB_ALT_TAU 4   // lazy-max threshold in binades (0: the reference's exact running max; measured on B200: 1307 / 1438 / 1452 TFLOP/s at tau 0 / 3 / 4)
 #endif
 
-// 128 x (96 + 96 + 48) = 30720 = the CTA's register pool (80 x 384); multiples of 16 (see attn_split.cu)
+// 128 x (96 + 96 + 48) = 30720 = the CTA's register pool (80 x 384)
 __device__ __forceinline__ void setmaxnreg_inc_96a() { asm volatile("setmaxnreg.inc.sync.aligned.u32 96;"); }
 // both softmax warpgroups (256 threads); barrier 0 is __syncthreads
 __device__ __forceinline__ void alt_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
